@@ -1,0 +1,14 @@
+"""sdr_b200 -- B200-native (sm_100a) streaming-FIR hot path of adamwalker/sdr behind the reference's own plugin API.
+
+Python here is only the host-side mirror of the reference's Haskell interface (records, constructors, Pipes) over
+the C ABI in ``include/sdr_b200.h``; all compute is in ``sdr_b200/lib/libsdr_b200.so`` (hand-written CUDA).
+"""
+from ._lib import (SDR_ARITH_EXACT, SDR_ARITH_FAST, SDR_DEVICE, SDR_HOST, SDR_HOST_PINNED, SdrError, LIB_PATH)  # noqa: F401
+from .device import Context, DeviceBuffer, Event, PinnedArray, device_count, has_cuda  # noqa: F401
+from .filter import (Decimator, Filter, NativePipe, Resampler, cudaDecimatorC, cudaDecimatorR, cudaDecimatorSymR,  # noqa: F401
+                     cudaFilterC, cudaFilterR, cudaFilterSymR, cudaResamplerC, cudaResamplerR, default_context,
+                     firDecimator, firFilter, firResampler, pipeFirDecimator, pipeFirFilter, pipeFirResampler)
+from .util import (complexFloatToInterleavedIQSigned2048, dcBlocker, fmDemod, fmDemodVec,  # noqa: F401
+                   interleavedIQSigned2048ToFloat, interleavedIQUnsignedByteToFloat, pipeConvertU8, pipeFmDemod,
+                   pipeScale, scaleFast)
+from . import multigpu  # noqa: F401

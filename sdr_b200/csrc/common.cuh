@@ -1,0 +1,86 @@
+// common.cuh -- shared declarations of the sdr_b200 native library (host + device).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/sdr_b200.h"
+
+namespace sdr {
+
+// ---- error plumbing -------------------------------------------------------------------------------------------
+int set_error(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SDR_CUDA(expr)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return ::sdr::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define SDR_TRY(expr)            \
+    do {                         \
+        int _s = (expr);         \
+        if (_s != SDR_OK) return _s; \
+    } while (0)
+
+// ---- context --------------------------------------------------------------------------------------------------
+struct Ctx {
+    int          device      = 0;
+    cudaStream_t stream      = nullptr;
+    cudaStream_t side        = nullptr;  // halo exchange / copy overlap
+    int          sm_count    = 0;
+    int          arith       = SDR_ARITH_FAST;
+    long long    launches    = 0;
+    // pinned + device staging for HOST-pointer calls (grown on demand)
+    void  *h_stage = nullptr; size_t h_stage_bytes = 0;
+    void  *d_stage_in = nullptr; size_t d_stage_in_bytes = 0;
+    void  *d_stage_out = nullptr; size_t d_stage_out_bytes = 0;
+    void  *d_flush = nullptr; size_t d_flush_bytes = 0;
+    int ensure_stage(size_t in_bytes, size_t out_bytes);
+    int bind() const;  // cudaSetDevice
+};
+
+// ---- a logically contiguous input made of up to two device segments (lastBuf ++ nextBuf) --------------------------
+struct Seg2 {
+    const void *a; long long na;  // first segment, na ELEMENTS (floats for real, float2 for complex)
+    const void *b; long long nb;  // second segment
+};
+
+// ---- kernel launchers (kernels_generic.cu) ----------------------------------------------------------------------
+// y[m] = sum_k c[k] x[m*D + k], m < num.  d_taps: T floats on device.  x = seg.a ++ seg.b, n_in = na + nb elements;
+// elements beyond n_in read as zero.
+int launch_fir_generic(Ctx *c, bool cplx, int T, int D, const float *d_taps, Seg2 seg, void *d_out, long long num);
+// same math, unfused mul+add in a reference variant's lane order.  W = SIMD width in floats (1 scalar, 4 SSE, 8 AVX);
+// layout 0 real / 1 complex duplicated-coefficient form / 2 complex "2" form; sym: T = half taps, pre-added samples.
+int launch_fir_exact_fir(Ctx *c, bool cplx, int T, int D, int W, int layout, int sym, const float *d_taps, Seg2 seg,
+                         void *d_out, long long num);
+// polyphase group-table resampler (resample.c:34-142): output i uses group (g0+i)%ng at input offset
+// ((g0+i)/ng)*sum_inc + prefix[(g0+i)%ng] - prefix[g0]; d_table [ng][row_stride]; d_prefix [ng]
+int launch_resample_groups(Ctx *c, bool cplx, int taps_per_group, int row_stride, int g0, int ng, const int *d_prefix,
+                           int sum_inc, const float *d_table, Seg2 seg, void *d_out, long long num);
+int launch_resample_exact(Ctx *c, bool cplx, int taps_per_group, int row_stride, int W, int layout, int g0, int ng,
+                          const int *d_prefix, int sum_inc, const float *d_table, Seg2 seg, void *d_out, long long num);
+int launch_convert_u8(Ctx *c, const uint8_t *d_in, float *d_out, long long n);
+int launch_convert_i16(Ctx *c, const int16_t *d_in, float *d_out, long long n);
+int launch_convert_tx(Ctx *c, const float *d_in, int16_t *d_out, long long n);
+int launch_scale(Ctx *c, float k, const float *d_in, float *d_out, long long n);
+int launch_fm_demod(Ctx *c, float last_re, float last_im, const float *d_in, float *d_out, long long n);
+int launch_fm_demod_carry(Ctx *c, const float *d_last, const float *d_in, float *d_out, long long n);
+int launch_dc_blocker(Ctx *c, float last_sample, float last_output, const float *d_in, float *d_out, long long n,
+                      float *d_final2);
+int launch_synth_noise(Ctx *c, float *d_out, long long n, long long first, uint32_t seed);
+int launch_synth_bytes(Ctx *c, uint8_t *d_out, long long n, long long first, uint32_t seed);
+int launch_checksum32(Ctx *c, const uint32_t *d_buf, long long n, long long first, unsigned long long *d_sum);
+int launch_fill(Ctx *c, void *d, size_t bytes);
+
+Ctx *default_ctx(int *status);   // per-thread context behind the reference-signature one-shot entry points
+
+// ---- tuned kernels (kernels_fast.cu) ------------------------------------------------------------------------------
+// complex data, real taps, decimate by D.  Returns SDR_OK and sets *done to the number of leading outputs it
+// produced (a multiple of its tile; 0 when the shape / alignment has no tuned kernel); the caller finishes the rest
+// with launch_fir_generic.  *name receives a static string naming the instantiation.
+int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_in, long long n_in, float *d_out,
+                      long long num, long long *done, const char **name);
+
+}  // namespace sdr

@@ -1,0 +1,203 @@
+// kernels_fast.cu -- tuned sm_100a kernels for the headline shapes.
+//
+// dec_c_ring<T, D, R>: complex data x real taps, decimate by D (reference decimate.c:73-113 `decimateRC` /
+// `decimateAVXRC`, reached from fastDecimatorC, Filter.hs:352-356).  y[m] = sum_k c[k] x[m*D + k].
+//
+// Design (DESIGN.md section "decimator kernel"):
+//   * persistent: one CTA per SM, 8 warps, each CTA walks a contiguous range of SUB-TILES (32*R outputs each).
+//   * the input stream is staged ONCE into a shared-memory ring of NS slots (one sub-tile = 32 lane segments of
+//     R*D complex samples) by TMA bulk copies (cp.async.bulk -> UBLKCP), completion on mbarriers; a slot is refilled
+//     by the warp that consumed it as soon as it and the neighbour that used its head as halo have arrived on the
+//     slot's `empty` barrier.  ~4 slots (64 KB) are in flight per SM.
+//   * lane l of a warp owns R consecutive outputs; its window is R + T/D - 1 decimation blocks (D samples) starting at
+//     its own segment.  Segments are padded by 16 B so the lanes' LDS.128 hit distinct bank groups.
+//   * taps live in T registers; the inner product is fully unrolled FFMA2 (fma.rn.f32x2: re and im of one sample
+//     in one instruction, tap broadcast), accumulation in increasing tap order -- the same order as the generic
+//     kernel, so the ragged tail finished by launch_fir_generic is computed identically.
+//   * no tensor cores (1-D dot products); the kernel needs 2*T/D = 32 FMA per 9 algorithmic bytes, i.e. it is
+//     balanced between HBM and the FP32 pipe (see DESIGN.md roofline).
+#include "common.cuh"
+
+namespace sdr {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 dup2(float v) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(v));
+    return d;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int T, int D, int R>
+struct RingCfg {
+    static_assert(T % D == 0 && D % 2 == 0, "taps must be a whole number of decimation blocks; D even");
+    static constexpr int JB = T / D;                        // tap blocks per output
+    static constexpr int BLK_BYTES = D * 8;                 // one decimation block of complex samples
+    static constexpr int SEG_BYTES = R * BLK_BYTES;         // the R blocks a lane owns
+    static constexpr int SEG_STRIDE = SEG_BYTES + 16;       // +16 B: lanes' LDS.128 land on distinct bank groups
+    static constexpr int SUB_OUT = 32 * R;                  // outputs per sub-tile (one warp pass)
+    static constexpr int SLOT_BYTES = 32 * SEG_STRIDE;
+    static constexpr int HALO_SEGS = (JB - 1 + R - 1) / R;  // segments of the NEXT sub-tile a pass reads
+    static constexpr int NWARPS = 8;
+    static constexpr int NS = (220 * 1024 - HALO_SEGS * SEG_STRIDE - 256) / SLOT_BYTES;   // ring slots
+    static constexpr int RING_BYTES = NS * SLOT_BYTES + HALO_SEGS * SEG_STRIDE;           // + mirror of slot 0's head
+    static constexpr int SMEM_BYTES = RING_BYTES + 2 * NS * 8 + 128;
+    static_assert(NS >= NWARPS + 3, "ring too small for 8 warps plus prefetch");
+    static_assert(HALO_SEGS <= 32, "halo wider than a sub-tile");
+};
+
+template <int T, int D, int R>
+__global__ void __launch_bounds__(256, 1)
+k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const float *__restrict__ taps, long long n_sub) {
+    typedef RingCfg<T, D, R> C;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // contiguous, balanced range of sub-tiles for this CTA
+    long long q = n_sub / gridDim.x, rem = n_sub % gridDim.x;
+    long long s0 = blockIdx.x * q + (blockIdx.x < rem ? blockIdx.x : rem);
+    int cnt = (int)(q + (blockIdx.x < rem ? 1 : 0));   // local sub-tiles 0..cnt-1 are computed; cnt is halo-only
+    if (cnt == 0) return;
+
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t bar_full = ring + C::RING_BYTES + ((128 - C::RING_BYTES % 128) % 128);
+    const uint32_t bar_empty = bar_full + C::NS * 8;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::NS; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned char *gin = reinterpret_cast<const unsigned char *>(in);
+    auto issue_fill = [&](int u) {
+        int slot = u % C::NS;
+        int nseg = (u == cnt) ? C::HALO_SEGS : 32;
+        uint32_t bytes = nseg * C::SEG_BYTES + (slot == 0 ? C::HALO_SEGS * C::SEG_BYTES : 0);
+        uint32_t bar = bar_full + 8 * slot;
+        if (lane == 0) mbar_expect_tx(bar, bytes);
+        __syncwarp();
+        const unsigned char *src = gin + (s0 + u) * (long long)(C::SUB_OUT * C::BLK_BYTES) + lane * C::SEG_BYTES;
+        if (lane < nseg) bulk_g2s(ring + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE, src, C::SEG_BYTES, bar);
+        if (slot == 0 && lane < C::HALO_SEGS)
+            bulk_g2s(ring + C::NS * C::SLOT_BYTES + lane * C::SEG_STRIDE, src, C::SEG_BYTES, bar);
+    };
+
+    for (int u = warp; u < C::NS && u <= cnt; u += C::NWARPS) issue_fill(u);
+
+    float tap[T];
+#pragma unroll
+    for (int k = 0; k < T; k++) tap[k] = __ldg(taps + k);
+
+    for (int u = warp; u < cnt; u += C::NWARPS) {
+        const int slot = u % C::NS, par = (u / C::NS) & 1;
+        const int slot2 = (u + 1) % C::NS, par2 = ((u + 1) / C::NS) & 1;
+        mbar_wait(bar_full + 8 * slot, par);
+        mbar_wait(bar_full + 8 * slot2, par2);
+
+        const unsigned char *base = smem + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE;
+        u64 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = 0ULL;
+#pragma unroll
+        for (int b = 0; b < R + C::JB - 1; b++) {
+            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(base + (b / R) * C::SEG_STRIDE + (b % R) * C::BLK_BYTES);
+            ulonglong2 v[D / 2];
+#pragma unroll
+            for (int i = 0; i < D / 2; i++) v[i] = p[i];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int j = b - r;
+                if (j < 0 || j >= C::JB) continue;
+#pragma unroll
+                for (int i = 0; i < D / 2; i++) {
+                    acc[r] = ffma2(v[i].x, dup2(tap[j * D + 2 * i]), acc[r]);
+                    acc[r] = ffma2(v[i].y, dup2(tap[j * D + 2 * i + 1]), acc[r]);
+                }
+            }
+        }
+        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + (s0 + u) * (long long)C::SUB_OUT + lane * R);
+#pragma unroll
+        for (int r = 0; r < R; r += 2) o[r / 2] = make_ulonglong2(acc[r], acc[r + 1]);
+
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bar_empty + 8 * slot);
+            if (u == 0) mbar_arrive(bar_empty + 8 * slot);   // sub-tile 0 has no predecessor using it as halo
+            mbar_arrive(bar_empty + 8 * slot2);
+        }
+        if (u + C::NS <= cnt) {
+            mbar_wait(bar_empty + 8 * slot, par);
+            issue_fill(u + C::NS);
+        }
+    }
+}
+
+template <int T, int D, int R>
+static int launch_ring(Ctx *c, const float *d_taps, const float *d_in, long long n_in, float *d_out, long long num,
+                       long long *done) {
+    typedef RingCfg<T, D, R> C;
+    static_assert(R % 2 == 0, "outputs per lane are stored in 16-byte pairs");
+    long long blocks_avail = n_in / D;
+    long long by_in = (blocks_avail - C::HALO_SEGS * R) / C::SUB_OUT;   // a pass also loads HALO_SEGS whole segments
+    long long n_sub = num / C::SUB_OUT;
+    if (by_in < n_sub) n_sub = by_in;
+    if (n_sub <= 0) { *done = 0; return SDR_OK; }
+    SDR_TRY(c->bind());
+    static thread_local int attr_dev = -1;
+    if (attr_dev != c->device) {
+        SDR_CUDA(cudaFuncSetAttribute(k_dec_c_ring<T, D, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_dev = c->device;
+    }
+    int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
+    k_dec_c_ring<T, D, R><<<grid, 256, C::SMEM_BYTES, c->stream>>>((const float2 *)d_in, (float2 *)d_out, d_taps, n_sub);
+    c->launches++;
+    SDR_CUDA(cudaGetLastError());
+    *done = n_sub * C::SUB_OUT;
+    return SDR_OK;
+}
+
+int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_in, long long n_in, float *d_out,
+                      long long num, long long *done, const char **name) {
+    *done = 0;
+    *name = "fir_direct";
+    if ((((uintptr_t)d_in | (uintptr_t)d_out) & 15) != 0) return SDR_OK;   // TMA bulk copies need 16-byte alignment
+    if (T == 128 && D == 8) {
+        *name = "dec_c_ring<128,8,8>";
+        return launch_ring<128, 8, 8>(c, d_taps, d_in, n_in, d_out, num, done);
+    }
+    return SDR_OK;
+}
+
+}  // namespace sdr

@@ -1,0 +1,246 @@
+// multigpu.cu -- sharding a flat stream over the GPUs of one box (the reference is single
+// process and has no counterpart -- the halo is what its `crossover` state carries between buffers,
+// hs_sources/SDR/Filter.hs:600-611), plus the synthetic-stream / checksum / L2-flush helpers of the C ABI.
+//
+// Each rank keeps one contiguous chunk of the input resident and owns the outputs whose windows START in it.  The
+// windows of its last (T - D) / D outputs run into the next rank's chunk: those T - D samples are the only data
+// exchanged (ncclSend to rank-1 / ncclRecv from rank+1 on a side stream) while the interior outputs are computed;
+// the boundary outputs follow once the halo has landed.  NCCL is bound at run time with dlopen so the library
+// loads (and every single-GPU path works) without it and shares the copy of libnccl a host process already has.
+#include "records.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace sdr {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static int nccl_api(NcclApi **out) {
+    static NcclApi api;
+    static int state = 0;   // 0 untried, 1 ok, -1 failed
+    if (state == 0) {
+        const char *names[] = {getenv("SDR_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            if (!n) continue;
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        state = -1;
+        if (api.lib) {
+#define SDR_SYM(field, name) *(void **)(&api.field) = dlsym(api.lib, name)
+            SDR_SYM(GetUniqueId, "ncclGetUniqueId");
+            SDR_SYM(CommInitRank, "ncclCommInitRank");
+            SDR_SYM(CommDestroy, "ncclCommDestroy");
+            SDR_SYM(GroupStart, "ncclGroupStart");
+            SDR_SYM(GroupEnd, "ncclGroupEnd");
+            SDR_SYM(Send, "ncclSend");
+            SDR_SYM(Recv, "ncclRecv");
+            SDR_SYM(GetErrorString, "ncclGetErrorString");
+#undef SDR_SYM
+            if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send &&
+                api.Recv && api.GetErrorString)
+                state = 1;
+        }
+    }
+    if (state != 1) return set_error(SDR_ENCCL, "NCCL not available: %s", api.lib ? "missing symbols" : dlerror());
+    *out = &api;
+    return SDR_OK;
+}
+
+#define SDR_NCCL(api, expr)                                                                       \
+    do {                                                                                          \
+        ncclResult_t _r = (expr);                                                                 \
+        if (_r != ncclSuccess) return set_error(SDR_ENCCL, "NCCL error %d (%s) in %s", (int)_r,   \
+                                                (api)->GetErrorString(_r), #expr);               \
+    } while (0)
+
+}  // namespace sdr
+
+using namespace sdr;
+
+struct sdr_comm {
+    Ctx *ctx = nullptr;
+    NcclApi *api = nullptr;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+    void *d_halo = nullptr;
+    size_t halo_bytes = 0;
+    cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
+};
+
+extern "C" {
+
+int sdr_shard_plan(long long n_samples, int taps, int factor, int world, int rank, sdr_shard_t *plan) {
+    if (!plan || n_samples < 0 || taps <= 0 || factor <= 0 || world <= 0 || rank < 0 || rank >= world)
+        return set_error(SDR_EINVAL, "sdr_shard_plan: bad argument");
+    long long total_out = n_samples >= taps ? (n_samples - taps) / factor + 1 : 0;
+    // chunk: ceil(N / world) rounded up to whole 256-output tiles so every rank's chunk starts tile- and 16-byte aligned
+    long long unit = 256LL * factor;
+    long long chunk = (n_samples + world - 1) / world;
+    chunk = ((chunk + unit - 1) / unit) * unit;
+    long long in_begin = chunk * rank;
+    if (in_begin > n_samples) in_begin = n_samples;
+    long long in_end = in_begin + chunk;
+    if (in_end > n_samples) in_end = n_samples;
+    long long out_begin = (in_begin + factor - 1) / factor;          // first window starting inside the chunk
+    long long out_end = (in_end + factor - 1) / factor;
+    if (out_end > total_out) out_end = total_out;
+    if (out_begin > out_end) out_begin = out_end;
+    plan->in_begin = in_begin;
+    plan->in_count = in_end - in_begin;
+    plan->out_begin = out_begin;
+    plan->out_count = out_end - out_begin;
+    long long last_needed = plan->out_count ? (out_end - 1) * factor + taps : in_end;   // one past the last sample read
+    plan->halo = last_needed > in_end ? last_needed - in_end : 0;
+    long long local0 = out_begin * factor - in_begin;                // offset of the first owned window in the chunk
+    long long interior = (plan->in_count - local0 >= taps) ? (plan->in_count - local0 - taps) / factor + 1 : 0;
+    plan->out_interior = interior < plan->out_count ? interior : plan->out_count;
+    plan->n_samples = n_samples; plan->taps = taps; plan->factor = factor; plan->world = world; plan->rank = rank;
+    return SDR_OK;
+}
+
+int sdr_comm_unique_id(unsigned char id[SDR_COMM_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) == SDR_COMM_ID_BYTES, "ncclUniqueId size");
+    NcclApi *api;
+    SDR_TRY(nccl_api(&api));
+    ncclUniqueId u;
+    SDR_NCCL(api, api->GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return SDR_OK;
+}
+
+int sdr_comm_create(sdr_ctx_t *ctx, const unsigned char id[SDR_COMM_ID_BYTES], int world, int rank, sdr_comm_t **out) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !id || !out || world <= 0 || rank < 0 || rank >= world) return set_error(SDR_EINVAL, "sdr_comm_create: bad argument");
+    *out = nullptr;
+    NcclApi *api;
+    SDR_TRY(nccl_api(&api));
+    SDR_TRY(c->bind());
+    sdr_comm *h = new sdr_comm();
+    h->ctx = c; h->api = api; h->world = world; h->rank = rank;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclResult_t r = api->CommInitRank(&h->comm, world, u, rank);
+    if (r != ncclSuccess) { delete h; return set_error(SDR_ENCCL, "ncclCommInitRank failed: %s", api->GetErrorString(r)); }
+    cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming);
+    *out = h;
+    return SDR_OK;
+}
+
+int sdr_comm_destroy(sdr_comm_t *c) {
+    if (!c) return SDR_OK;
+    c->ctx->bind();
+    cudaStreamSynchronize(c->ctx->stream);
+    cudaStreamSynchronize(c->ctx->side);
+    if (c->comm) c->api->CommDestroy(c->comm);
+    if (c->d_halo) cudaFree(c->d_halo);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    delete c;
+    return SDR_OK;
+}
+
+int sdr_decimate_sharded(sdr_decimator_t *d, sdr_comm_t *c, const sdr_shard_t *plan, const void *d_in, void *d_out) {
+    if (!d || !plan || (plan->in_count && !d_in) || (plan->out_count && !d_out))
+        return set_error(SDR_EINVAL, "sdr_decimate_sharded: bad argument");
+    FirRec &r = d->r;
+    Ctx *ctx = r.ctx;
+    if (plan->taps != r.T || plan->factor != r.D)
+        return set_error(SDR_EINVAL, "sdr_decimate_sharded: plan was made for %d taps / %d, decimator has %d / %d", plan->taps,
+                         plan->factor, r.T, r.D);
+    if (plan->world > 1 && (!c || c->world != plan->world || c->rank != plan->rank || c->ctx != ctx))
+        return set_error(SDR_EINVAL, "sdr_decimate_sharded: communicator does not match the plan");
+    SDR_TRY(ctx->bind());
+    const size_t eb = elem_bytes(r.cplx);
+    const long long local0 = plan->out_begin * plan->factor - plan->in_begin;
+    bool exchange = false;
+    if (plan->world > 1) {
+        // what my left neighbour needs from the head of my chunk
+        sdr_shard_t left;
+        long long send = 0;
+        if (plan->rank > 0) { SDR_TRY(sdr_shard_plan(plan->n_samples, plan->taps, plan->factor, plan->world, plan->rank - 1, &left));
+                              send = left.halo; }
+        if (send > plan->in_count)
+            return set_error(SDR_EPRECOND, "sdr_decimate_sharded: chunk of %lld samples is shorter than the %lld-sample halo",
+                             plan->in_count, send);
+        long long recv = plan->halo;
+        if (send || recv) {
+            exchange = true;
+            if ((size_t)recv * eb > c->halo_bytes) {
+                if (c->d_halo) { SDR_CUDA(cudaStreamSynchronize(ctx->side)); SDR_CUDA(cudaFree(c->d_halo)); }
+                c->halo_bytes = (size_t)recv * eb + 256;
+                SDR_CUDA(cudaMalloc(&c->d_halo, c->halo_bytes));
+            }
+            // the chunk was produced on the main stream: the side stream must not send it early
+            SDR_CUDA(cudaEventRecord(c->ev_ready, ctx->stream));
+            SDR_CUDA(cudaStreamWaitEvent(ctx->side, c->ev_ready, 0));
+            SDR_NCCL(c->api, c->api->GroupStart());
+            if (send) SDR_NCCL(c->api, c->api->Send(d_in, (size_t)send * eb, ncclChar, plan->rank - 1, c->comm, ctx->side));
+            if (recv) SDR_NCCL(c->api, c->api->Recv(c->d_halo, (size_t)recv * eb, ncclChar, plan->rank + 1, c->comm, ctx->side));
+            SDR_NCCL(c->api, c->api->GroupEnd());
+            SDR_CUDA(cudaEventRecord(c->ev_halo, ctx->side));
+        }
+    }
+    // interior: every window that lies inside the resident chunk
+    if (plan->out_interior > 0) {
+        Seg2 seg = {d_in, plan->in_count, nullptr, 0};
+        SDR_TRY(r.run(seg, local0, d_out, plan->out_interior, false));
+    }
+    // boundary: windows that run into the halo
+    long long nb = plan->out_count - plan->out_interior;
+    if (nb > 0) {
+        if (!exchange) return set_error(SDR_EPRECOND, "sdr_decimate_sharded: boundary outputs without a neighbour");
+        SDR_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_halo, 0));
+        Seg2 seg = {d_in, plan->in_count, c->d_halo, plan->halo};
+        SDR_TRY(r.run(seg, local0 + plan->out_interior * plan->factor, (char *)d_out + (size_t)plan->out_interior * eb, nb, false));
+    } else if (exchange) {
+        SDR_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_halo, 0));   // keep the send ordered before later writes to d_in
+    }
+    return SDR_OK;
+}
+
+// ---- synthetic streams + measurement helpers -----------------------------------------------------------------------
+int sdr_synth_noise(sdr_ctx_t *ctx, float *d_out, long long n_floats, long long first_float, uint32_t seed) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || n_floats < 0 || (n_floats && !d_out)) return set_error(SDR_EINVAL, "sdr_synth_noise: bad argument");
+    return launch_synth_noise(c, d_out, n_floats, first_float, seed);
+}
+int sdr_synth_bytes(sdr_ctx_t *ctx, uint8_t *d_out, long long n_bytes, long long first_byte, uint32_t seed) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || n_bytes < 0 || (n_bytes && !d_out)) return set_error(SDR_EINVAL, "sdr_synth_bytes: bad argument");
+    return launch_synth_bytes(c, d_out, n_bytes, first_byte, seed);
+}
+int sdr_flush_l2(sdr_ctx_t *ctx) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return set_error(SDR_EINVAL, "sdr_flush_l2: null ctx");
+    SDR_TRY(c->bind());
+    if (!c->d_flush) { c->d_flush_bytes = (size_t)256 << 20; SDR_CUDA(cudaMalloc(&c->d_flush, c->d_flush_bytes)); }
+    return launch_fill(c, c->d_flush, c->d_flush_bytes);
+}
+int sdr_checksum32(sdr_ctx_t *ctx, const void *d_buf, long long n_words, long long first_word, uint64_t *sum) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !sum || n_words < 0 || (n_words && !d_buf)) return set_error(SDR_EINVAL, "sdr_checksum32: bad argument");
+    SDR_TRY(c->bind());
+    SDR_TRY(c->ensure_stage(0, 64));
+    unsigned long long *d_sum = (unsigned long long *)c->d_stage_out;
+    SDR_TRY(launch_checksum32(c, (const uint32_t *)d_buf, n_words, first_word, d_sum));
+    unsigned long long h = 0;
+    SDR_CUDA(cudaMemcpyAsync(&h, d_sum, 8, cudaMemcpyDeviceToHost, c->stream));
+    SDR_CUDA(cudaStreamSynchronize(c->stream));
+    *sum = h;
+    return SDR_OK;
+}
+
+}  // extern "C"
