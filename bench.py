@@ -291,6 +291,7 @@ def run_e2e(args, ctx, dec, plan, rank, world, dist, sdr_b200, L):
 
     def one_pass():
         pipe = sdr_b200.pipeFirDecimator(dec, BUF)
+        L.check(L.lib.sdr_pipe_set_batch(pipe.h, args.e2e_batch_vectors * BUF))
         L.check(L.lib.sdr_pipe_run(pipe.h, pipe.h, hin.p, BUF, n_vecs, L.SDR_HOST_PINNED, hout.p, out_cap, L.SDR_HOST_PINNED,
                                    C.byref(n_out)))
         pipe.close()
@@ -336,7 +337,8 @@ def run_e2e(args, ctx, dec, plan, rank, world, dist, sdr_b200, L):
         total = n_vecs * BUF
     res = {"value": total / (ms / steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(8 * n_vecs * BUF),
            "d2h_bytes_per_step": int(8 * got), "steps": steps,
-           "api": "sdr_pipe_run(firDecimator, 8192-sample pinned host vectors in, 8192-sample host vectors out)",
+           "api": "sdr_pipe_run(firDecimator, 8192-sample pinned host vectors in, 8192-sample host vectors out), "
+                  f"sdr_pipe_set_batch = {args.e2e_batch_vectors} output vectors per launch",
            "spot_parity_vs_reference_avx": ok}
     hin.free()
     hout.free()
@@ -353,6 +355,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-batch-vectors", type=int, default=64,
+                    help="sdr_pipe_set_batch: output vectors per launch in the end-to-end run (64 x 8192 outputs = 32 MiB of input per DMA)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
 

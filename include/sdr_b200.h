@@ -249,12 +249,17 @@ int sdr_pipe_destroy(sdr_pipe_t *p);
 int sdr_pipe_push(sdr_pipe_t *p, const void *in, long long n, int mem);
 /* number of complete output vectors ready to pop */
 int sdr_pipe_ready(sdr_pipe_t *p, int *n_blocks);
-/* copy out the next output vector; elementwise pipes (fm_demod/convert/scale) yield one vector per pushed
+/* length in elements of the vector the next sdr_pipe_pop will deliver (SDR_EAGAIN when none is ready) */
+int sdr_pipe_next_len(sdr_pipe_t *p, long long *n);
+/* copy out the next output vector (`out` must hold sdr_pipe_next_len elements); elementwise pipes (fm_demod/convert/scale) yield one vector per pushed
  * vector with that vector's length (returned in *n_out).  SDR_EAGAIN when none is ready. */
 int sdr_pipe_pop(sdr_pipe_t *p, void *out, long long *n_out, int mem);
 /* issue any deferred SDR_HOST_PINNED copies and wait for everything enqueued on the pipe's stream: after this the
  * caller may reuse the pinned vectors it pushed and read pinned / device vectors it popped */
 int sdr_pipe_sync(sdr_pipe_t *p);
+/* throughput knob for FIR stages: do not launch before `min_outputs` new outputs are computable (default 0 = as soon
+ * as one output vector can be completed, the lowest latency).  Yielded vectors are unchanged, only their timing. */
+int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs);
 /* `runEffect $ each vectors >-> p >-> ... >-> sink >-> collect` as one native loop: pushes n_vecs consecutive vectors of
  * vec_len input elements starting at `in` into `p`, pops every vector `sink` yields (sink = p, or the last stage
  * connected behind it) into `out` back to back, then sdr_pipe_sync.  *n_out = elements written (<= out_capacity). */

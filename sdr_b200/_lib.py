@@ -136,6 +136,8 @@ _sig("sdr_pipe_ready", _P, C.POINTER(_I))
 _sig("sdr_pipe_pop", _P, _P, C.POINTER(_LL), _I)
 _sig("sdr_pipe_connect", _P, _P)
 _sig("sdr_pipe_sync", _P)
+_sig("sdr_pipe_set_batch", _P, _LL)
+_sig("sdr_pipe_next_len", _P, C.POINTER(_LL))
 _sig("sdr_pipe_run", _P, _P, _P, _LL, _LL, _I, _P, _LL, _I, C.POINTER(_LL))
 
 _sig("sdr_shard_plan", _LL, _I, _I, _I, _I, C.POINTER(ShardPlan))

@@ -69,6 +69,7 @@ struct sdr_pipe {
     const char *assert_name = "";
     // SDR_HOST_PINNED pushes: host-to-device copies of vectors that are contiguous on both sides are merged and
     // issued only when a launch needs the data (one DMA per output vector instead of one per input vector)
+    long long batch_min = 0;          // launch only once this many new outputs are computable (0: one output vector)
     const char *pend_src = nullptr;
     char *pend_dst = nullptr;
     size_t pend_bytes = 0;
@@ -94,9 +95,16 @@ static int forward(sdr_pipe *p) {
     if (is_fir_kind(p->kind)) {
         long long have = (long long)(p->fifo.size() / p->out_eb);
         long long nb = have / p->block_out;
-        if (nb > 0) {
+        if (nb > 0 && is_fir_kind(p->downstream->kind)) {
+            // a FIR stage only sees the flat stream: hand it all complete vectors as one contiguous push
             SDR_TRY(pipe_push_dev(p->downstream, p->fifo.p + p->fifo.rd, nb * p->block_out));
             p->fifo.consume((size_t)(nb * p->block_out) * p->out_eb);
+        } else {
+            // element-wise stages yield one vector per awaited vector: keep the vector structure
+            for (long long b = 0; b < nb; b++) {
+                SDR_TRY(pipe_push_dev(p->downstream, p->fifo.p + p->fifo.rd, p->block_out));
+                p->fifo.consume((size_t)p->block_out * p->out_eb);
+            }
         }
     } else {
         while (!p->vec_lens.empty()) {
@@ -110,15 +118,17 @@ static int forward(sdr_pipe *p) {
 }
 
 // run whatever the stream now allows (FIR kinds); data already appended to p->in
-static int process_fir(sdr_pipe *p) {
+static int process_fir(sdr_pipe *p, bool force = false) {
     long long have = (long long)(p->in.size() / p->in_eb);
+    const long long fifo_have = (long long)(p->fifo.size() / p->out_eb);
+    const long long batch = (force || p->batch_min < p->block_out) ? p->block_out : p->batch_min;
     if (p->kind == P_RESAMP) {
         ResRec &r = *p->res;
         long long total_out = (p->n_total * r.L >= r.T) ? (p->n_total * r.L - r.T) / r.M + 1 : 0;
         long long count = total_out - p->k_next;
         // lazy: launch only when the new outputs complete at least one output vector (fewer, larger launches;
         // invisible to the caller because vectors are only ever yielded whole)
-        if (count > 0 && (long long)(p->fifo.size() / p->out_eb) + count >= p->block_out) {
+        if (count > 0 && fifo_have + count >= p->block_out && (fifo_have + count >= batch)) {
             SDR_TRY(flush_pending(p));
             long long i_k = (p->k_next * r.M + r.L - 1) / r.L;   // ceil(k M / L): first sample of output k
             SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
@@ -135,7 +145,7 @@ static int process_fir(sdr_pipe *p) {
     }
     FirRec &f = *p->fir;
     long long count = (have >= f.T) ? (have - f.T) / f.D + 1 : 0;
-    if (count > 0 && (long long)(p->fifo.size() / p->out_eb) + count >= p->block_out) {
+    if (count > 0 && fifo_have + count >= p->block_out && (fifo_have + count >= batch)) {
         SDR_TRY(flush_pending(p));
         SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
         Seg2 seg = {p->in.p + p->in.rd, have, nullptr, 0};
@@ -292,6 +302,18 @@ int sdr_pipe_ready(sdr_pipe_t *p, int *n_blocks) {
     return SDR_OK;
 }
 
+int sdr_pipe_next_len(sdr_pipe_t *p, long long *n) {
+    if (!p || !n) return set_error(SDR_EINVAL, "sdr_pipe_next_len: bad argument");
+    if (is_fir_kind(p->kind)) {
+        if ((long long)(p->fifo.size() / p->out_eb) < p->block_out) return set_error(SDR_EAGAIN, "sdr_pipe_next_len: no complete output block yet");
+        *n = p->block_out;
+    } else {
+        if (p->vec_lens.empty()) return set_error(SDR_EAGAIN, "sdr_pipe_next_len: no output vector yet");
+        *n = p->vec_lens.front();
+    }
+    return SDR_OK;
+}
+
 int sdr_pipe_pop(sdr_pipe_t *p, void *out, long long *n_out, int mem) {
     if (!p || !out || mem < SDR_HOST || mem > SDR_HOST_PINNED) return set_error(SDR_EINVAL, "sdr_pipe_pop: bad argument");
     long long n;
@@ -322,26 +344,54 @@ int sdr_pipe_sync(sdr_pipe_t *p) {
     return SDR_OK;
 }
 
+int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs) {
+    if (!p || min_outputs < 0) return set_error(SDR_EINVAL, "sdr_pipe_set_batch: bad argument");
+    p->batch_min = min_outputs;
+    return SDR_OK;
+}
+
+// pop every complete vector of `sink` into out[written...] with ONE copy (FIR kinds) / one copy per vector otherwise
+static int drain(sdr_pipe *sink, void *out, long long out_capacity, int out_mem, long long *written) {
+    if (is_fir_kind(sink->kind)) {
+        long long nb = (long long)(sink->fifo.size() / sink->out_eb) / sink->block_out;
+        if (nb == 0) return SDR_OK;
+        long long n = nb * sink->block_out;
+        if (*written + n > out_capacity) return set_error(SDR_EINVAL, "sdr_pipe_run: output capacity %lld too small", out_capacity);
+        SDR_CUDA(cudaMemcpyAsync((char *)out + (size_t)*written * sink->out_eb, sink->fifo.p + sink->fifo.rd, (size_t)n * sink->out_eb,
+                                 out_mem == SDR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sink->ctx->stream));
+        if (out_mem == SDR_HOST) SDR_CUDA(cudaStreamSynchronize(sink->ctx->stream));
+        sink->fifo.consume((size_t)n * sink->out_eb);
+        *written += n;
+        return SDR_OK;
+    }
+    while (!sink->vec_lens.empty()) {
+        if (*written + sink->vec_lens.front() > out_capacity)
+            return set_error(SDR_EINVAL, "sdr_pipe_run: output capacity %lld too small", out_capacity);
+        long long got = 0;
+        SDR_TRY(sdr_pipe_pop(sink, (char *)out + (size_t)*written * sink->out_eb, &got, out_mem));
+        *written += got;
+    }
+    return SDR_OK;
+}
+
 // runEffect $ each vectors >-> p >-> ... >-> sink >-> collect, as one native loop
 int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_len, long long n_vecs, int in_mem,
                  void *out, long long out_capacity, int out_mem, long long *n_out) {
-    if (!p || !sink || vec_len <= 0 || n_vecs < 0 || (n_vecs && !in) || (out_capacity && !out) || !n_out)
+    if (!p || !sink || vec_len <= 0 || n_vecs < 0 || (n_vecs && !in) || (out_capacity && !out) || !n_out ||
+        in_mem < SDR_HOST || in_mem > SDR_HOST_PINNED || out_mem < SDR_HOST || out_mem > SDR_HOST_PINNED)
         return set_error(SDR_EINVAL, "sdr_pipe_run: bad argument");
     long long written = 0;
+    SDR_TRY(p->ctx->bind());
     for (long long v = 0; v < n_vecs; v++) {
-        SDR_TRY(sdr_pipe_push(p, (const char *)in + (size_t)(v * vec_len) * p->in_eb, vec_len, in_mem));
-        for (;;) {
-            int ready = 0;
-            SDR_TRY(sdr_pipe_ready(sink, &ready));
-            if (!ready) break;
-            long long next_len = is_fir_kind(sink->kind) ? sink->block_out : sink->vec_lens.front();
-            if (written + next_len > out_capacity)
-                return set_error(SDR_EINVAL, "sdr_pipe_run: output capacity %lld too small", out_capacity);
-            long long got = 0;
-            SDR_TRY(sdr_pipe_pop(sink, (char *)out + (size_t)written * sink->out_eb, &got, out_mem));
-            written += got;
-        }
+        SDR_TRY(pipe_push_any(p, (const char *)in + (size_t)(v * vec_len) * p->in_eb, vec_len, in_mem));
+        SDR_TRY(drain(sink, out, out_capacity, out_mem, &written));
     }
+    // end of input: run what the batching knob was still holding back, stage by stage
+    for (sdr_pipe *q = p; q; q = q->downstream) {
+        if (is_fir_kind(q->kind)) { SDR_TRY(process_fir(q, true)); SDR_TRY(forward(q)); }
+        if (q == sink) break;
+    }
+    SDR_TRY(drain(sink, out, out_capacity, out_mem, &written));
     SDR_TRY(sdr_pipe_sync(p));
     *n_out = written;
     return SDR_OK;

@@ -221,9 +221,10 @@ class NativePipe:
         L.check(L.lib.sdr_pipe_ready(self.h, C.byref(n)))
         return n.value
 
-    def pop(self, capacity):
-        out = np.empty(capacity, self.out_dtype)
+    def pop(self, capacity=None):
         n = C.c_longlong()
+        L.check(L.lib.sdr_pipe_next_len(self.h, C.byref(n)))
+        out = np.empty(n.value, self.out_dtype)
         L.check(L.lib.sdr_pipe_pop(self.h, L.ptr(out), C.byref(n), L.SDR_HOST))
         return out[:n.value]
 

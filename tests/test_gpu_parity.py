@@ -307,7 +307,7 @@ def test_resampler_record_in_reference_state_machine(sdr, cplx):
 
 @pytest.mark.parametrize("cplx,T,D,block_out,sizes", [
     (True, 128, 8, 8192, [8192] * 16),                       # cfg2: one output vector per 8 input vectors
-    (True, 128, 8, 1000, [8192, 3001, 128, 9000, 20000]),    # ragged, minimum-length vector
+    (True, 128, 8, 1000, [8192, 3001, 300, 9000, 20000]),    # ragged (the reference itself asserts on vectors too close to numCoeffs)
     (False, 128, 8, 512, [8192, 777, 4096]),
     (True, 51, 8, 256, [4096] * 5),                          # the FM example's RF decimator length
 ])
@@ -323,7 +323,7 @@ def test_native_decimator_pipe_vs_reference_pipe(sdr, cplx, T, D, block_out, siz
         close(np.concatenate(got), np.concatenate(want))
 
 
-@pytest.mark.parametrize("sizes", [[8192] * 4, [8192, 64, 5000, 64, 64, 9999]])
+@pytest.mark.parametrize("sizes", [[8192] * 4, [8192, 200, 5000, 150, 130, 9999]])
 def test_native_filter_pipe_vs_reference_pipe(sdr, sizes):
     half = taps_for(32, 8)
     x = rnd(sum(sizes), False, 7)
@@ -336,7 +336,7 @@ def test_native_filter_pipe_vs_reference_pipe(sdr, sizes):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
-@pytest.mark.parametrize("sizes", [[8192] * 4, [8192, 100, 5000, 33, 12000]])
+@pytest.mark.parametrize("sizes", [[8192] * 4, [8192, 200, 5000, 133, 12000]])
 def test_native_resampler_pipe_vs_reference_pipe(sdr, cplx, sizes):
     taps = taps_for(90, 9)
     x = rnd(sum(sizes), cplx, 8)
