@@ -28,7 +28,11 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 struct Ctx {
     int          device      = 0;
     cudaStream_t stream      = nullptr;
-    cudaStream_t side        = nullptr;  // halo exchange / copy overlap
+    cudaStream_t side        = nullptr;  // halo exchange / ragged-tail overlap
+    cudaStream_t override_st = nullptr;  // when set, kernel launchers enqueue here instead of `stream`
+    cudaEvent_t  ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t s() const { return override_st ? override_st : stream; }
+    int          reserve_sms = 0;        // SMs the persistent kernels leave free (for a concurrent NCCL kernel)
     int          sm_count    = 0;
     int          arith       = SDR_ARITH_FAST;
     long long    launches    = 0;

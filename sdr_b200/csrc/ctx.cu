@@ -112,6 +112,8 @@ int sdr_ctx_create(int device, sdr_ctx_t **ctx) {
     SDR_CUDA(cudaSetDevice(device));
     SDR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SDR_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    SDR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    SDR_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     *ctx = reinterpret_cast<sdr_ctx_t *>(c);
     return SDR_OK;
 }
@@ -126,6 +128,8 @@ int sdr_ctx_destroy(sdr_ctx_t *ctx) {
     if (c->d_stage_in) cudaFree(c->d_stage_in);
     if (c->d_stage_out) cudaFree(c->d_stage_out);
     if (c->d_flush) cudaFree(c->d_flush);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->side);
     delete c;

@@ -180,8 +180,10 @@ static int launch_ring(Ctx *c, const float *d_taps, const float *d_in, long long
         SDR_CUDA(cudaFuncSetAttribute(k_dec_c_ring<T, D, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_dev = c->device;
     }
-    int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
-    k_dec_c_ring<T, D, R><<<grid, 256, C::SMEM_BYTES, c->stream>>>((const float2 *)d_in, (float2 *)d_out, d_taps, n_sub);
+    int sms = c->sm_count - c->reserve_sms;
+    if (sms < 1) sms = 1;
+    int grid = (int)(n_sub < sms ? n_sub : sms);
+    k_dec_c_ring<T, D, R><<<grid, 256, C::SMEM_BYTES, c->s()>>>((const float2 *)d_in, (float2 *)d_out, d_taps, n_sub);
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     *done = n_sub * C::SUB_OUT;

@@ -105,8 +105,8 @@ static int launch_direct(Ctx *c, bool cplx, OutMap m, int T, const float *d_taps
     if (num <= 0) return SDR_OK;
     SDR_TRY(c->bind());
     int grid = grid_for(num, 256, c->sm_count, 32);
-    if (cplx) k_fir_direct<true><<<grid, 256, 0, c->stream>>>(m, T, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
-    else      k_fir_direct<false><<<grid, 256, 0, c->stream>>>(m, T, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
+    if (cplx) k_fir_direct<true><<<grid, 256, 0, c->s()>>>(m, T, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
+    else      k_fir_direct<false><<<grid, 256, 0, c->s()>>>(m, T, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -198,8 +198,8 @@ int launch_fir_exact(Ctx *c, bool cplx, OutMap m, int T, int W, int layout, int 
     if (!(W == 1 || W == 4 || W == 8)) return set_error(SDR_EINVAL, "exact arithmetic: lane width %d not in {1,4,8}", W);
     SDR_TRY(c->bind());
     int grid = grid_for(num, 128, c->sm_count, 32);
-    if (cplx) k_fir_exact<true><<<grid, 128, 0, c->stream>>>(m, T, W, layout, sym, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
-    else      k_fir_exact<false><<<grid, 128, 0, c->stream>>>(m, T, W, layout, sym, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
+    if (cplx) k_fir_exact<true><<<grid, 128, 0, c->s()>>>(m, T, W, layout, sym, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
+    else      k_fir_exact<false><<<grid, 128, 0, c->s()>>>(m, T, W, layout, sym, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -241,10 +241,10 @@ int launch_convert_u8(Ctx *c, const uint8_t *d_in, float *d_out, long long n) {
     SDR_TRY(c->bind());
     long long nv = 0;
     if ((((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0) nv = n / 16;
-    if (nv) { k_convert_u8_vec<<<grid_for(nv, 256, c->sm_count), 256, 0, c->stream>>>((const uint4 *)d_in, (float4 *)d_out, nv);
+    if (nv) { k_convert_u8_vec<<<grid_for(nv, 256, c->sm_count), 256, 0, c->s()>>>((const uint4 *)d_in, (float4 *)d_out, nv);
               SDR_LAUNCH_CHECK(c); }
     long long rest = n - nv * 16;
-    if (rest) { k_convert_u8<<<grid_for(rest, 256, c->sm_count), 256, 0, c->stream>>>(d_in + nv * 16, d_out + nv * 16, rest);
+    if (rest) { k_convert_u8<<<grid_for(rest, 256, c->sm_count), 256, 0, c->s()>>>(d_in + nv * 16, d_out + nv * 16, rest);
                 SDR_LAUNCH_CHECK(c); }
     return SDR_OK;
 }
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) k_convert_i16(const int16_t *__restrict__
 int launch_convert_i16(Ctx *c, const int16_t *d_in, float *d_out, long long n) {
     if (n <= 0) return SDR_OK;
     SDR_TRY(c->bind());
-    k_convert_i16<<<grid_for(n, 256, c->sm_count), 256, 0, c->stream>>>(d_in, d_out, n);
+    k_convert_i16<<<grid_for(n, 256, c->sm_count), 256, 0, c->s()>>>(d_in, d_out, n);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) k_convert_tx(const float *__restrict__ in
 int launch_convert_tx(Ctx *c, const float *d_in, int16_t *d_out, long long n) {
     if (n <= 0) return SDR_OK;
     SDR_TRY(c->bind());
-    k_convert_tx<<<grid_for(n, 256, c->sm_count), 256, 0, c->stream>>>(d_in, d_out, n);
+    k_convert_tx<<<grid_for(n, 256, c->sm_count), 256, 0, c->s()>>>(d_in, d_out, n);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -296,10 +296,10 @@ int launch_scale(Ctx *c, float k, const float *d_in, float *d_out, long long n) 
     SDR_TRY(c->bind());
     long long nv = 0;
     if ((((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0) nv = n / 4;
-    if (nv) { k_scale_vec<<<grid_for(nv, 256, c->sm_count), 256, 0, c->stream>>>(k, (const float4 *)d_in, (float4 *)d_out, nv);
+    if (nv) { k_scale_vec<<<grid_for(nv, 256, c->sm_count), 256, 0, c->s()>>>(k, (const float4 *)d_in, (float4 *)d_out, nv);
               SDR_LAUNCH_CHECK(c); }
     long long rest = n - nv * 4;
-    if (rest) { k_scale<<<grid_for(rest, 256, c->sm_count), 256, 0, c->stream>>>(k, d_in + nv * 4, d_out + nv * 4, rest);
+    if (rest) { k_scale<<<grid_for(rest, 256, c->sm_count), 256, 0, c->s()>>>(k, d_in + nv * 4, d_out + nv * 4, rest);
                 SDR_LAUNCH_CHECK(c); }
     return SDR_OK;
 }
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) k_fm_demod(float last_re, float last_im, 
 int launch_fm_demod(Ctx *c, float last_re, float last_im, const float *d_in, float *d_out, long long n) {
     if (n <= 0) return SDR_OK;
     SDR_TRY(c->bind());
-    k_fm_demod<<<grid_for(n, 256, c->sm_count), 256, 0, c->stream>>>(last_re, last_im, nullptr, (const float2 *)d_in, d_out, n);
+    k_fm_demod<<<grid_for(n, 256, c->sm_count), 256, 0, c->s()>>>(last_re, last_im, nullptr, (const float2 *)d_in, d_out, n);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -342,7 +342,7 @@ int launch_fm_demod(Ctx *c, float last_re, float last_im, const float *d_in, flo
 int launch_fm_demod_carry(Ctx *c, const float *d_last, const float *d_in, float *d_out, long long n) {
     if (n <= 0) return SDR_OK;
     SDR_TRY(c->bind());
-    k_fm_demod<<<grid_for(n, 256, c->sm_count), 256, 0, c->stream>>>(0.0f, 0.0f, (const float2 *)d_last, (const float2 *)d_in, d_out, n);
+    k_fm_demod<<<grid_for(n, 256, c->sm_count), 256, 0, c->s()>>>(0.0f, 0.0f, (const float2 *)d_last, (const float2 *)d_in, d_out, n);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last
 int launch_dc_blocker(Ctx *c, float last_sample, float last_output, const float *d_in, float *d_out, long long n,
                       float *d_final2) {
     SDR_TRY(c->bind());
-    k_dc_blocker<<<1, 32, 0, c->stream>>>(last_sample, last_output, d_in, d_out, n, d_final2);
+    k_dc_blocker<<<1, 32, 0, c->s()>>>(last_sample, last_output, d_in, d_out, n, d_final2);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) k_synth_noise(float *__restrict__ out, lo
 int launch_synth_noise(Ctx *c, float *d_out, long long n, long long first, uint32_t seed) {
     if (n <= 0) return SDR_OK;
     SDR_TRY(c->bind());
-    k_synth_noise<<<grid_for(n, 256, c->sm_count), 256, 0, c->stream>>>(d_out, n, first, seed);
+    k_synth_noise<<<grid_for(n, 256, c->sm_count), 256, 0, c->s()>>>(d_out, n, first, seed);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256) k_synth_bytes(uint8_t *__restrict__ out, 
 int launch_synth_bytes(Ctx *c, uint8_t *d_out, long long n, long long first, uint32_t seed) {
     if (n <= 0) return SDR_OK;
     SDR_TRY(c->bind());
-    k_synth_bytes<<<grid_for(n, 256, c->sm_count), 256, 0, c->stream>>>(d_out, n, first, seed);
+    k_synth_bytes<<<grid_for(n, 256, c->sm_count), 256, 0, c->s()>>>(d_out, n, first, seed);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -431,9 +431,9 @@ __global__ void __launch_bounds__(256) k_checksum32(const uint32_t *__restrict__
 }
 int launch_checksum32(Ctx *c, const uint32_t *d_buf, long long n, long long first, unsigned long long *d_sum) {
     SDR_TRY(c->bind());
-    SDR_CUDA(cudaMemsetAsync(d_sum, 0, 8, c->stream));
+    SDR_CUDA(cudaMemsetAsync(d_sum, 0, 8, c->s()));
     if (n <= 0) return SDR_OK;
-    k_checksum32<<<grid_for(n, 256, c->sm_count), 256, 0, c->stream>>>(d_buf, n, first, d_sum);
+    k_checksum32<<<grid_for(n, 256, c->sm_count), 256, 0, c->s()>>>(d_buf, n, first, d_sum);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256) k_fill(uint4 *__restrict__ p, long long n
 }
 int launch_fill(Ctx *c, void *d, size_t bytes) {
     SDR_TRY(c->bind());
-    k_fill<<<grid_for((long long)(bytes / 16), 256, c->sm_count), 256, 0, c->stream>>>((uint4 *)d, (long long)(bytes / 16), 0x5d2b200u);
+    k_fill<<<grid_for((long long)(bytes / 16), 256, c->sm_count), 256, 0, c->s()>>>((uint4 *)d, (long long)(bytes / 16), 0x5d2b200u);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }

@@ -84,9 +84,12 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
     }
     long long done = 0;
     last_kernel = "fir_direct";
+    const bool can_fork = cplx && ctx->override_st == nullptr;
     if (cplx) {
         // tuned kernel over the part of the FIRST segment it can take; the rest (ragged tail, straddling windows)
-        // is finished by the generic kernel in the same tap order
+        // is finished by the generic kernel in the same tap order.  The tail only depends on the INPUT, so it runs
+        // on the side stream concurrently with the tuned kernel (fork before, join after).
+        if (can_fork) SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
         const char *name = nullptr;
         SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, (const float *)seg.a, seg.na, (float *)d_out, num, &done, &name));
         if (done > 0) last_kernel = name;
@@ -97,7 +100,14 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
         if (skip >= rest.na) { rest.a = (const char *)rest.b + (skip - rest.na) * eb; rest.na = rest.nb - (skip - rest.na);
                                rest.b = nullptr; rest.nb = 0; if (rest.na < 0) rest.na = 0; }
         else                 { rest.a = (const char *)rest.a + skip * eb; rest.na -= skip; }
-        SDR_TRY(launch_fir_generic(ctx, cplx, T, D, d_taps, rest, (char *)d_out + done * eb, num - done));
+        const bool fork = can_fork && done > 0;
+        if (fork) { SDR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0)); ctx->override_st = ctx->side; }
+        int rc = launch_fir_generic(ctx, cplx, T, D, d_taps, rest, (char *)d_out + done * eb, num - done);
+        if (fork) {
+            ctx->override_st = nullptr;
+            if (rc == SDR_OK) { SDR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side)); SDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
+        }
+        SDR_TRY(rc);
     }
     return SDR_OK;
 }
