@@ -245,7 +245,8 @@ def run_gpu(args, rank, world, local_rank, dist):
     achieved = ALGO_BYTES_PER_SAMPLE * plan.in_count / ((ms / args.steps) * 1e-3) / 1e9
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (traffic or {}).get("dram_bytes_per_launch"), "kernel": kernel_name, "peak_source": peak_src,
+                "traffic": ((traffic or {}).get("dram_bytes_per_input_sample") or 0) * plan.in_count or None,
+                "kernel": kernel_name, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * plan.in_count,
                 "note": "duration = CUDA events on the library's stream over the timed region / steps (ring kernel + ragged-tail launch)"}
     if traffic:

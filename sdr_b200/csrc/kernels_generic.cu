@@ -13,6 +13,9 @@
 //   dc blocker        y[n] = x[n] - x[n-1] + 0.997 y[n-1]                filter.c:152-161
 #include "common.cuh"
 
+#include <cstdlib>
+#include <type_traits>
+
 namespace sdr {
 
 static inline int grid_for(long long n, int block, int sm_count, int per_sm = 16) {
@@ -101,9 +104,81 @@ __global__ void __launch_bounds__(256) k_fir_direct(OutMap m, int T, const float
     }
 }
 
+// Tiled form of the same computation: a CTA stages the input span of 128 consecutive outputs (and the tap rows) in
+// shared memory with coalesced loads, then each thread runs the identical sequential FMA chain out of shared memory.
+// One global round trip per tile instead of one per tap: this is what the small ragged-tail / halo-boundary launches
+// and every shape without a tuned kernel run on.
+constexpr int TILE_OUT = 128;
+
+template <bool CPLX>
+__global__ void __launch_bounds__(TILE_OUT) k_fir_tile(OutMap m, int T, int n_rows, const float *__restrict__ taps,
+                                                       const void *__restrict__ a, long long na,
+                                                       const void *__restrict__ b, long long nb,
+                                                       void *__restrict__ out, long long num) {
+    typedef typename std::conditional<CPLX, float2, float>::type E;
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    const int row_floats = (m.ng == 0) ? T : m.row_stride;
+    float *ts = reinterpret_cast<float *>(tile_smem);
+    E *xs = reinterpret_cast<E *>(tile_smem + (((size_t)n_rows * row_floats * 4 + 15) / 16) * 16);
+    for (int i = threadIdx.x; i < n_rows * row_floats; i += TILE_OUT) ts[i] = __ldg(taps + i);
+    const long long n_tiles = (num + TILE_OUT - 1) / TILE_OUT;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long o0 = tile * TILE_OUT;
+        const int n_o = (int)((num - o0) < TILE_OUT ? (num - o0) : TILE_OUT);
+        long long start0, start_last; int row;
+        map_output(m, o0, &start0, &row);
+        map_output(m, o0 + n_o - 1, &start_last, &row);
+        const int span = (int)(start_last - start0) + T;
+        __syncthreads();   // previous tile fully consumed (and taps visible on the first trip)
+        for (int i = threadIdx.x; i < span; i += TILE_OUT) xs[i] = seg_at<E>((const E *)a, na, (const E *)b, nb, start0 + i);
+        __syncthreads();
+        if ((int)threadIdx.x < n_o) {
+            long long start;
+            map_output(m, o0 + threadIdx.x, &start, &row);
+            const E *x = xs + (start - start0);
+            const float *c = ts + row * row_floats;
+            if (CPLX) {
+                float re = 0.0f, im = 0.0f;
+#pragma unroll 8
+                for (int k = 0; k < T; k++) { float2 v = ((const float2 *)x)[k]; float t = c[k];
+                                              re = fmaf(t, v.x, re); im = fmaf(t, v.y, im); }
+                ((float2 *)out)[o0 + threadIdx.x] = make_float2(re, im);
+            } else {
+                float acc = 0.0f;
+#pragma unroll 8
+                for (int k = 0; k < T; k++) acc = fmaf(c[k], ((const float *)x)[k], acc);
+                ((float *)out)[o0 + threadIdx.x] = acc;
+            }
+        }
+    }
+}
+
 static int launch_direct(Ctx *c, bool cplx, OutMap m, int T, const float *d_taps, Seg2 seg, void *d_out, long long num) {
     if (num <= 0) return SDR_OK;
     SDR_TRY(c->bind());
+    // shared-memory need of the tiled kernel: tap rows + the widest input span of one tile
+    const int n_rows = (m.ng == 0) ? 1 : m.ng;
+    const int row_floats = (m.ng == 0) ? T : m.row_stride;
+    long long span;
+    if (m.ng == 0) span = (long long)(TILE_OUT - 1) * m.D + T;
+    else           span = ((long long)(TILE_OUT - 1) / m.ng + 2) * m.sum_inc + T;
+    size_t smem = (((size_t)n_rows * row_floats * 4 + 15) / 16) * 16 + (size_t)span * (cplx ? 8 : 4);
+    static const bool no_tile = getenv("SDR_B200_NOTILE") != nullptr;   // debugging aid: force the direct kernel
+    if (smem <= 200 * 1024 && !no_tile) {
+        static thread_local int attr_dev = -1;
+        if (attr_dev != c->device) {
+            SDR_CUDA(cudaFuncSetAttribute(k_fir_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SDR_CUDA(cudaFuncSetAttribute(k_fir_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_dev = c->device;
+        }
+        long long tiles = (num + TILE_OUT - 1) / TILE_OUT;
+        long long cap = (long long)c->sm_count * (smem > 48 * 1024 ? 1 : 8);
+        int grid = (int)(tiles < cap ? tiles : cap);
+        if (cplx) k_fir_tile<true><<<grid, TILE_OUT, smem, c->s()>>>(m, T, n_rows, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
+        else      k_fir_tile<false><<<grid, TILE_OUT, smem, c->s()>>>(m, T, n_rows, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
+        SDR_LAUNCH_CHECK(c);
+        return SDR_OK;
+    }
     int grid = grid_for(num, 256, c->sm_count, 32);
     if (cplx) k_fir_direct<true><<<grid, 256, 0, c->s()>>>(m, T, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);
     else      k_fir_direct<false><<<grid, 256, 0, c->s()>>>(m, T, d_taps, seg.a, seg.na, seg.b, seg.nb, d_out, num);

@@ -192,33 +192,32 @@ int sdr_decimate_sharded(sdr_decimator_t *d, sdr_comm_t *c, const sdr_shard_t *p
             SDR_NCCL(c->api, c->api->GroupEnd());
         }
     }
-    // interior: every window that lies inside the resident chunk (main stream; its ragged tail forks to the side stream)
     const char *kernel = r.last_kernel;
-    if (plan->out_interior > 0) {
+    if (!exchange) {   // single rank (or nothing to exchange): plain stream pass
+        if (plan->out_count > plan->out_interior) return set_error(SDR_EPRECOND, "sdr_decimate_sharded: boundary outputs without a neighbour");
         Seg2 seg = {d_in, plan->in_count, nullptr, 0};
-        // the NCCL send/recv kernel cannot share an SM with a CTA of the persistent decimator (registers): leave it a
-        // few SMs, otherwise the CTAs queued behind it start only after the rendezvous and stretch the whole pass
-        ctx->reserve_sms = exchange ? 4 : 0;
-        int rc = r.run(seg, local0, d_out, plan->out_interior, false);
-        ctx->reserve_sms = 0;
+        return r.run(seg, local0, d_out, plan->out_count, false);
+    }
+    // main stream: the tuned kernel over every sub-tile that lies inside the resident chunk.  The NCCL send/recv kernel
+    // cannot share an SM with a CTA of the persistent decimator (registers): leave it a few SMs, otherwise the CTAs
+    // queued behind it start only after the rendezvous and stretch the whole pass.
+    long long done = 0;
+    ctx->reserve_sms = 4;
+    int rc = r.run_tuned(d_in, plan->in_count, local0, d_out, plan->out_interior, &done);
+    ctx->reserve_sms = 0;
+    SDR_TRY(rc);
+    if (done > 0) kernel = r.last_kernel;
+    // side stream, right behind the receive: ONE generic launch for the ragged end of the interior plus the windows
+    // that run into the halo; the main stream joins once at the end.
+    if (plan->out_count > done) {
+        Seg2 seg = {d_in, plan->in_count, c->d_halo, plan->halo};
+        ctx->override_st = ctx->side;
+        rc = r.run(seg, local0 + done * plan->factor, (char *)d_out + (size_t)done * eb, plan->out_count - done, false);
+        ctx->override_st = nullptr;
         SDR_TRY(rc);
-        kernel = r.last_kernel;
     }
-    // boundary: windows that run into the halo -- on the side stream, right behind the receive, so the main stream
-    // only joins once at the end
-    long long nb = plan->out_count - plan->out_interior;
-    if (nb > 0 && !exchange) return set_error(SDR_EPRECOND, "sdr_decimate_sharded: boundary outputs without a neighbour");
-    if (exchange) {
-        if (nb > 0) {
-            Seg2 seg = {d_in, plan->in_count, c->d_halo, plan->halo};
-            ctx->override_st = ctx->side;
-            int rc = r.run(seg, local0 + plan->out_interior * plan->factor, (char *)d_out + (size_t)plan->out_interior * eb, nb, false);
-            ctx->override_st = nullptr;
-            SDR_TRY(rc);
-        }
-        SDR_CUDA(cudaEventRecord(c->ev_halo, ctx->side));
-        SDR_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_halo, 0));   // also keeps the send ordered before later writes to d_in
-    }
+    SDR_CUDA(cudaEventRecord(c->ev_halo, ctx->side));
+    SDR_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_halo, 0));   // also keeps the send ordered before later writes to d_in
     r.last_kernel = kernel;
     return SDR_OK;
 }

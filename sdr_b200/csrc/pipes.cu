@@ -347,6 +347,14 @@ int sdr_pipe_sync(sdr_pipe_t *p) {
 int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs) {
     if (!p || min_outputs < 0) return set_error(SDR_EINVAL, "sdr_pipe_set_batch: bad argument");
     p->batch_min = min_outputs;
+    if (is_fir_kind(p->kind) && min_outputs > 0) {
+        // size both buffers for the batch once, instead of growing by doubling while the stream runs
+        SDR_TRY(p->ctx->bind());
+        long long in_per_out = (p->kind == P_RESAMP) ? (p->res->M + p->res->L - 1) / p->res->L : p->fir->D;
+        long long taps = (p->kind == P_RESAMP) ? p->res->T : p->fir->T;
+        SDR_TRY(p->in.reserve((size_t)(2 * (min_outputs + p->block_out) * in_per_out + taps) * p->in_eb));
+        SDR_TRY(p->fifo.reserve((size_t)(2 * (min_outputs + p->block_out)) * p->out_eb));
+    }
     return SDR_OK;
 }
 

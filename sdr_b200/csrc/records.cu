@@ -84,7 +84,8 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
     }
     long long done = 0;
     last_kernel = "fir_direct";
-    const bool can_fork = cplx && ctx->override_st == nullptr;
+    static const bool no_fork = getenv("SDR_B200_NOFORK") != nullptr;   // debugging aid: keep the tail on the main stream
+    const bool can_fork = cplx && ctx->override_st == nullptr && !no_fork;
     if (cplx) {
         // tuned kernel over the part of the FIRST segment it can take; the rest (ragged tail, straddling windows)
         // is finished by the generic kernel in the same tap order.  The tail only depends on the INPUT, so it runs
@@ -109,6 +110,16 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
         }
         SDR_TRY(rc);
     }
+    return SDR_OK;
+}
+
+int FirRec::run_tuned(const void *d_in, long long n_in, long long first, void *d_out, long long num, long long *done) {
+    *done = 0;
+    if (num <= 0 || !cplx || arith != SDR_ARITH_FAST) return SDR_OK;
+    const char *name = nullptr;
+    SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, (const float *)((const char *)d_in + first * 8), n_in - first, (float *)d_out, num,
+                              done, &name));
+    if (*done > 0) last_kernel = name;
     return SDR_OK;
 }
 

@@ -24,6 +24,8 @@ struct FirRec {
     void destroy();
     // y[m] = sum_k c[k] x[first + m*D + k], x = seg.a ++ seg.b (zeros beyond), m < num.  `first` in elements.
     int run(Seg2 seg, long long first, void *d_out, long long num, bool cross_order);
+    // tuned kernel only, over the leading outputs it can take from the single segment (*done of them); nothing else
+    int run_tuned(const void *d_in, long long n_in, long long first, void *d_out, long long num, long long *done);
 };
 
 struct ResRec {
