@@ -193,11 +193,15 @@ int sdr_filter_create(sdr_ctx_t *ctx, int is_complex, const float *coeffs, int n
 int sdr_filter_create_sym(sdr_ctx_t *ctx, int is_complex, const float *half_coeffs, int half_len, sdr_filter_t **f);
 int sdr_filter_destroy(sdr_filter_t *f);
 int sdr_filter_num_coeffs(const sdr_filter_t *f); /* numCoeffsF */
+const char *sdr_filter_last_kernel(const sdr_filter_t *f); /* kernel the last call on this handle dispatched to */
 /* filterOne  :: Int -> v a -> vm a -> m ()            (Filter.hs:118) */
 int sdr_filter_one(sdr_filter_t *f, int count, const void *in, void *out, int mem);
 /* filterCross :: Int -> v a -> v a -> vm a -> m ()    (Filter.hs:119; FilterInternal.hs:405-408) */
 int sdr_filter_cross(sdr_filter_t *f, int count, const void *last, int n_last, const void *next, int n_next,
                      void *out, int mem);
+
+/* whole device-resident stream in one call: y[n], n < num, over n_in resident samples (enqueue-only) */
+int sdr_filter_stream(sdr_filter_t *f, const void *d_in, long long n_in, void *d_out, long long num);
 
 /* fastDecimatorR / fastDecimatorC / fastDecimatorSymR (Filter.hs:311-315,352-356,385-389) */
 int sdr_decimator_create(sdr_ctx_t *ctx, int is_complex, int factor, const float *coeffs, int num_coeffs,
@@ -211,6 +215,9 @@ int sdr_decimator_factor(const sdr_decimator_t *d);     /* decimationD */
 int sdr_decimate_one(sdr_decimator_t *d, int count, const void *in, void *out, int mem);
 int sdr_decimate_cross(sdr_decimator_t *d, int count, const void *last, int n_last, const void *next, int n_next,
                        void *out, int mem);
+/* whole device-resident stream in one call: y[m], m < num, over n_in resident samples (enqueue-only); what bench.py
+ * times and what the interior of a multi-GPU shard runs */
+int sdr_decimate_stream(sdr_decimator_t *d, const void *d_in, long long n_in, void *d_out, long long num);
 /* name of the kernel the last sdr_decimate_one on this handle dispatched to ("dec_c_fast<...>", "fir_generic", ...) */
 const char *sdr_decimator_last_kernel(const sdr_decimator_t *d);
 
@@ -221,11 +228,14 @@ int sdr_resampler_create(sdr_ctx_t *ctx, int is_complex, int interpolation, int 
                          int num_coeffs, int size_multiple, sdr_resampler_t **r);
 int sdr_resampler_destroy(sdr_resampler_t *r);
 int sdr_resampler_num_coeffs(const sdr_resampler_t *r);    /* numCoeffsR (Filter.hs:422) */
+const char *sdr_resampler_last_kernel(const sdr_resampler_t *r);
 int sdr_resampler_interpolation(const sdr_resampler_t *r); /* interpolationR */
 int sdr_resampler_decimation(const sdr_resampler_t *r);    /* decimationR */
 /* resampleOne :: dat -> Int -> v a -> vm a -> m (dat, Int) (Filter.hs:142); *end_offset = the Int */
 int sdr_resample_one(sdr_resampler_t *r, sdr_resampler_dat_t *dat, int count, const void *in, void *out, int mem,
                      int *end_offset);
+/* whole device-resident stream in one call, from output 0 of the stream (group 0): enqueue-only */
+int sdr_resample_stream(sdr_resampler_t *r, const void *d_in, long long n_in, void *d_out, long long num);
 /* resampleCross (Filter.hs:143; FilterInternal.hs:411-423) */
 int sdr_resample_cross(sdr_resampler_t *r, sdr_resampler_dat_t *dat, int count, const void *last, int n_last,
                        const void *next, int n_next, void *out, int mem, int *end_offset);

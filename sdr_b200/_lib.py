@@ -35,6 +35,10 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 lib.sdr_last_error.restype = C.c_char_p
 lib.sdr_decimator_last_kernel.restype = C.c_char_p
+lib.sdr_filter_last_kernel.restype = C.c_char_p
+lib.sdr_resampler_last_kernel.restype = C.c_char_p
+lib.sdr_filter_last_kernel.argtypes = [C.c_void_p]
+lib.sdr_resampler_last_kernel.argtypes = [C.c_void_p]
 
 c_void_pp = C.POINTER(C.c_void_p)
 _f32p = C.POINTER(C.c_float)
@@ -115,6 +119,8 @@ _sig("sdr_decimator_factor", _P)
 _sig("sdr_decimate_one", _P, _I, _P, _P, _I)
 _sig("sdr_decimate_cross", _P, _I, _P, _I, _P, _I, _P, _I)
 _sig("sdr_decimate_stream", _P, _P, _LL, _P, _LL)
+_sig("sdr_filter_stream", _P, _P, _LL, _P, _LL)
+_sig("sdr_resample_stream", _P, _P, _LL, _P, _LL)
 lib.sdr_decimator_last_kernel.argtypes = [_P]
 _sig("sdr_resampler_create", _P, _I, _I, _I, _P, _I, _I, c_void_pp)
 _sig("sdr_resampler_destroy", _P)

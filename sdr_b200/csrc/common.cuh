@@ -87,4 +87,11 @@ Ctx *default_ctx(int *status);   // per-thread context behind the reference-sign
 int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_in, long long n_in, float *d_out,
                       long long num, long long *done, const char **name);
 
+// real data, stride-1 FIR (kernels_real.cu); same contract as launch_dec_c_fast
+int launch_fir_r_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_in, long long n_in, float *d_out,
+                      long long num, long long *done, const char **name);
+// real rational resampler: output 0 is phase 0 and its window starts at d_in; d_plain_taps = the n_taps plain taps
+int launch_res_r_fast(Ctx *c, int L, int M, int n_taps, const float *d_plain_taps, const float *d_in, long long n_in,
+                      float *d_out, long long num, long long *done, const char **name);
+
 }  // namespace sdr

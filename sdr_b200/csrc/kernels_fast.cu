@@ -16,48 +16,9 @@
 //     kernel, so the ragged tail finished by launch_fir_generic is computed identically.
 //   * no tensor cores (1-D dot products); the kernel needs 2*T/D = 32 FMA per 9 algorithmic bytes, i.e. it is
 //     balanced between HBM and the FP32 pipe (see DESIGN.md roofline).
-#include "common.cuh"
+#include "ring_common.cuh"
 
 namespace sdr {
-
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ u64 dup2(float v) {
-    u64 d;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(v));
-    return d;
-}
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 
 template <int T, int D, int R>
 struct RingCfg {
@@ -72,7 +33,7 @@ struct RingCfg {
     static constexpr int NWARPS = 8;
     static constexpr int NS = (220 * 1024 - HALO_SEGS * SEG_STRIDE - 256) / SLOT_BYTES;   // ring slots
     static constexpr int RING_BYTES = NS * SLOT_BYTES + HALO_SEGS * SEG_STRIDE;           // + mirror of slot 0's head
-    static constexpr int SMEM_BYTES = RING_BYTES + 2 * NS * 8 + 128;
+    static constexpr int SMEM_BYTES = RING_BYTES + 2 * NS * 8 + NS * 4 + 256;
     static_assert(NS >= NWARPS + 3, "ring too small for 8 warps plus prefetch");
     static_assert(HALO_SEGS <= 32, "halo wider than a sub-tile");
 };
@@ -93,8 +54,10 @@ k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const floa
     const uint32_t ring = smem_u32(smem);
     const uint32_t bar_full = ring + C::RING_BYTES + ((128 - C::RING_BYTES % 128) % 128);
     const uint32_t bar_empty = bar_full + C::NS * 8;
+    const uint32_t gen_armed = bar_empty + C::NS * 8;   // generation guard, see ring_common.cuh
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::NS; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2); }
+        for (int s = 0; s < C::NS; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2);
+                                          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(gen_armed + 4 * s), "r"(0) : "memory"); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -112,6 +75,7 @@ k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const floa
         if (lane < nseg) bulk_g2s(ring + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE, src, C::SEG_BYTES, bar);
         if (slot == 0 && lane < C::HALO_SEGS)
             bulk_g2s(ring + C::NS * C::SLOT_BYTES + lane * C::SEG_STRIDE, src, C::SEG_BYTES, bar);
+        if (lane == 0) gen_publish(gen_armed + 4 * slot, u / C::NS + 1);
     };
 
     for (int u = warp; u < C::NS && u <= cnt; u += C::NWARPS) issue_fill(u);
@@ -123,7 +87,9 @@ k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const floa
     for (int u = warp; u < cnt; u += C::NWARPS) {
         const int slot = u % C::NS, par = (u / C::NS) & 1;
         const int slot2 = (u + 1) % C::NS, par2 = ((u + 1) / C::NS) & 1;
+        gen_wait(gen_armed + 4 * slot, u / C::NS + 1);
         mbar_wait(bar_full + 8 * slot, par);
+        gen_wait(gen_armed + 4 * slot2, (u + 1) / C::NS + 1);
         mbar_wait(bar_full + 8 * slot2, par2);
 
         const unsigned char *base = smem + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE;

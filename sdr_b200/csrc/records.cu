@@ -85,14 +85,15 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
     long long done = 0;
     last_kernel = "fir_direct";
     static const bool no_fork = getenv("SDR_B200_NOFORK") != nullptr;   // debugging aid: keep the tail on the main stream
-    const bool can_fork = cplx && ctx->override_st == nullptr && !no_fork;
-    if (cplx) {
+    const bool can_fork = ctx->override_st == nullptr && !no_fork;
+    {
         // tuned kernel over the part of the FIRST segment it can take; the rest (ragged tail, straddling windows)
         // is finished by the generic kernel in the same tap order.  The tail only depends on the INPUT, so it runs
         // on the side stream concurrently with the tuned kernel (fork before, join after).
         if (can_fork) SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
         const char *name = nullptr;
-        SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, (const float *)seg.a, seg.na, (float *)d_out, num, &done, &name));
+        if (cplx) SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, (const float *)seg.a, seg.na, (float *)d_out, num, &done, &name));
+        else      SDR_TRY(launch_fir_r_fast(ctx, T, D, d_taps, (const float *)seg.a, seg.na, (float *)d_out, num, &done, &name));
         if (done > 0) last_kernel = name;
     }
     if (done < num) {
@@ -162,6 +163,8 @@ int ResRec::create(Ctx *c, bool is_complex, int interpolation, int decimation, c
     }
     SDR_CUDA(cudaMalloc(&d_table, sizeof(float) * table.size()));
     SDR_CUDA(cudaMalloc(&d_prefix, sizeof(int) * ng));
+    SDR_CUDA(cudaMalloc(&d_plain, sizeof(float) * n));
+    SDR_CUDA(cudaMemcpyAsync(d_plain, coeffs, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
     SDR_CUDA(cudaMemcpyAsync(d_table, table.data(), sizeof(float) * table.size(), cudaMemcpyHostToDevice, c->stream));
     SDR_CUDA(cudaMemcpyAsync(d_prefix, prefix.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, c->stream));
     SDR_CUDA(cudaStreamSynchronize(c->stream));
@@ -169,8 +172,8 @@ int ResRec::create(Ctx *c, bool is_complex, int interpolation, int decimation, c
 }
 
 void ResRec::destroy() {
-    if (ctx) { ctx->bind(); if (d_table) cudaFree(d_table); if (d_prefix) cudaFree(d_prefix); }
-    d_table = nullptr; d_prefix = nullptr;
+    if (ctx) { ctx->bind(); if (d_table) cudaFree(d_table); if (d_prefix) cudaFree(d_prefix); if (d_plain) cudaFree(d_plain); }
+    d_table = nullptr; d_prefix = nullptr; d_plain = nullptr;
 }
 
 int ResRec::group_of_offset(int offset) const {
@@ -189,6 +192,47 @@ int ResRec::run(Seg2 seg, long long first, int g0, void *d_out, long long num, b
         int W = cross_order ? 1 : 8, layout = cplx ? 2 : 0;
         int nt = cross_order ? group_len : row_stride;
         return launch_resample_exact(ctx, cplx, nt, row_stride, W, layout, g0, ng, d_prefix, sum_inc, d_table, seg, d_out, num);
+    }
+    last_kernel = "fir_tile";
+    // tuned kernel for real streams: it starts on a cycle boundary (phase 0) with a 16-byte aligned window, so a short
+    // generic prefix brings the stream there, the tuned kernel takes the bulk, the generic kernel the ragged end
+    static const bool no_tuned = getenv("SDR_B200_NOTUNED") != nullptr;   // debugging aid
+    if (!cplx && ng == L && num >= 4096 && !no_tuned) {
+        auto span = [&](long long count) { long long gi = (long long)g0 + count;
+                                           return (gi / ng) * sum_inc + prefix[gi % ng] - prefix[g0]; };
+        long long p0 = -1;
+        for (long long p = 0; p <= 4LL * ng; p++)
+            if ((g0 + p) % ng == 0 && span(p) < seg.na && ((((uintptr_t)seg.a) + (size_t)span(p) * 4) & 15) == 0) { p0 = p; break; }
+        if (p0 >= 0 && p0 < num) {
+            long long done = 0;
+            const char *name = nullptr;
+            const bool can_fork = ctx->override_st == nullptr;
+            if (can_fork) SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            SDR_TRY(launch_res_r_fast(ctx, L, M, n_taps, d_plain, (const float *)seg.a + span(p0), seg.na - span(p0),
+                                      (float *)d_out + p0, num - p0, &done, &name));
+            if (done > 0) {
+                last_kernel = name;
+                const bool fork = can_fork;
+                if (fork) { SDR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0)); ctx->override_st = ctx->side; }
+                int rc = SDR_OK;
+                if (p0 > 0) rc = launch_resample_groups(ctx, cplx, group_len, row_stride, g0, ng, d_prefix, sum_inc, d_table, seg, d_out, p0);
+                long long k2 = p0 + done;   // first output of the ragged end; (g0 + k2) % ng == 0 again
+                if (rc == SDR_OK && k2 < num) {
+                    Seg2 rest = seg;
+                    long long skip = span(k2);
+                    if (skip >= rest.na) { rest.a = (const char *)rest.b + (skip - rest.na) * eb; rest.na = rest.nb - (skip - rest.na);
+                                           rest.b = nullptr; rest.nb = 0; if (rest.na < 0) rest.na = 0; }
+                    else                 { rest.a = (const char *)rest.a + skip * eb; rest.na -= skip; }
+                    rc = launch_resample_groups(ctx, cplx, group_len, row_stride, (int)((g0 + k2) % ng), ng, d_prefix, sum_inc, d_table,
+                                                rest, (char *)d_out + k2 * eb, num - k2);
+                }
+                if (fork) {
+                    ctx->override_st = nullptr;
+                    if (rc == SDR_OK) { SDR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side)); SDR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); }
+                }
+                return rc;
+            }
+        }
     }
     return launch_resample_groups(ctx, cplx, group_len, row_stride, g0, ng, d_prefix, sum_inc, d_table, seg, d_out, num);
 }
@@ -480,6 +524,7 @@ int sdr_filter_create_sym(sdr_ctx_t *ctx, int is_complex, const float *half_coef
 }
 int sdr_filter_destroy(sdr_filter_t *f) { if (f) { f->r.destroy(); delete f; } return SDR_OK; }
 int sdr_filter_num_coeffs(const sdr_filter_t *f) { return f ? f->r.T : -1; }
+const char *sdr_filter_last_kernel(const sdr_filter_t *f) { return f ? f->r.last_kernel : "none"; }
 
 static int rec_one(FirRec &r, const char *who, int count, const void *in, void *out, int mem) {
     if (count < 0 || (count && (!in || !out)) || (mem != SDR_HOST && mem != SDR_DEVICE))
@@ -576,6 +621,15 @@ int sdr_decimate_stream(sdr_decimator_t *d, const void *d_in, long long n_in, vo
     return d->r.run(seg, 0, d_out, num, false);
 }
 
+int sdr_filter_stream(sdr_filter_t *f, const void *d_in, long long n_in, void *d_out, long long num) {
+    if (!f || num < 0 || n_in < 0 || (num && (!d_in || !d_out))) return set_error(SDR_EINVAL, "sdr_filter_stream: bad argument");
+    if (num && (num - 1) + f->r.T > n_in)
+        return set_error(SDR_EPRECOND, "sdr_filter_stream: %lld outputs need %lld samples, %lld resident", num, (num - 1) + f->r.T, n_in);
+    SDR_TRY(f->r.ctx->bind());
+    Seg2 seg = {d_in, n_in, nullptr, 0};
+    return f->r.run(seg, 0, d_out, num, false);
+}
+
 // ---- layer 2: Resampler ------------------------------------------------------------------------------------------
 int sdr_resampler_create(sdr_ctx_t *ctx, int is_complex, int interpolation, int decimation, const float *coeffs,
                          int num_coeffs, int size_multiple, sdr_resampler_t **r) {
@@ -589,6 +643,7 @@ int sdr_resampler_create(sdr_ctx_t *ctx, int is_complex, int interpolation, int 
 }
 int sdr_resampler_destroy(sdr_resampler_t *r) { if (r) { r->r.destroy(); delete r; } return SDR_OK; }
 int sdr_resampler_num_coeffs(const sdr_resampler_t *r) { return r ? r->r.T : -1; }
+const char *sdr_resampler_last_kernel(const sdr_resampler_t *r) { return r ? r->r.last_kernel : "none"; }
 int sdr_resampler_interpolation(const sdr_resampler_t *r) { return r ? r->r.L : -1; }
 int sdr_resampler_decimation(const sdr_resampler_t *r) { return r ? r->r.M : -1; }
 
@@ -620,6 +675,18 @@ int sdr_resample_one(sdr_resampler_t *h, sdr_resampler_dat_t *dat, int count, co
     dat->group = group; dat->offset = offset;
     if (end_offset) *end_offset = offset;
     return SDR_OK;
+}
+
+// whole device-resident stream in one call, starting at output 0 of the stream (group 0, offset 0)
+int sdr_resample_stream(sdr_resampler_t *h, const void *d_in, long long n_in, void *d_out, long long num) {
+    if (!h || num < 0 || n_in < 0 || (num && (!d_in || !d_out))) return set_error(SDR_EINVAL, "sdr_resample_stream: bad argument");
+    ResRec &r = h->r;
+    if (num && res_span(r, 0, num - 1) + r.group_len > n_in)
+        return set_error(SDR_EPRECOND, "sdr_resample_stream: %lld outputs need %lld samples, %lld resident", num,
+                         res_span(r, 0, num - 1) + r.group_len, n_in);
+    SDR_TRY(r.ctx->bind());
+    Seg2 seg = {d_in, n_in, nullptr, 0};
+    return r.run(seg, 0, 0, d_out, num, false);
 }
 
 int sdr_resample_cross(sdr_resampler_t *h, sdr_resampler_dat_t *dat, int count, const void *last, int n_last,

@@ -42,6 +42,8 @@ struct ResRec {
     std::vector<int> inc, prefix, offset_of_group;
     float *d_table = nullptr;  // [ng][row_stride]
     int   *d_prefix = nullptr; // [ng]
+    float *d_plain = nullptr;  // the n_taps plain coefficients (tuned kernels index them as c[f + l L])
+    const char *last_kernel = "none";
     int create(Ctx *c, bool is_complex, int interpolation, int decimation, const float *coeffs, int n, int size_multiple);
     void destroy();
     int group_of_offset(int offset) const;

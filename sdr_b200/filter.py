@@ -45,6 +45,9 @@ class Filter:
     handle: Any
     ctx: Context
 
+    def last_kernel(self):
+        return L.lib.sdr_filter_last_kernel(self.handle).decode()
+
     def __del__(self):
         if L is not None and self.handle:
             L.lib.sdr_filter_destroy(self.handle)
@@ -83,6 +86,9 @@ class Resampler:
     cplx: bool
     handle: Any
     ctx: Context
+
+    def last_kernel(self):
+        return L.lib.sdr_resampler_last_kernel(self.handle).decode()
 
     def __del__(self):
         if L is not None and self.handle:

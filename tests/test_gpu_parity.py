@@ -445,6 +445,62 @@ def test_stream_decimator_tuned_vs_generic_and_oracle(sdr, L, ctx, ref, log2n):
         b_.free()
 
 
+@pytest.mark.parametrize("T", [64, 32, 128])
+@pytest.mark.parametrize("log2n", [18, 26])
+def test_stream_real_filter_tuned_vs_generic_and_oracle(sdr, L, ctx, ref, T, log2n):
+    """cfg1 at full size: ring kernel == generic kernel bit for bit (same summation order), windows vs reference AVX"""
+    n = 1 << log2n
+    half = synth.windowed_sinc_taps(T, 1 / 4)[:T // 2]
+    f = sdr.cudaFilterSymR(half)
+    num = n - T + 1
+    x = ctx.alloc(4 * n + 64)
+    y = ctx.alloc(4 * num + 64)
+    y2 = ctx.alloc(4 * num + 64)
+    ctx.synth_noise(x, n)
+    L.check(L.lib.sdr_filter_stream(f.handle, x.ptr, n, y.ptr, num))
+    assert f.last_kernel().startswith("fir_r_ring"), f.last_kernel()
+    ctx.synth_noise(x, n, first_float=0, offset_bytes=4)   # same stream, 4-byte shifted: not 16-byte aligned -> generic
+    L.check(L.lib.sdr_filter_stream(f.handle, x.at(4), n, y2.ptr, num))
+    assert not f.last_kernel().startswith("fir_r_ring")
+    assert ctx.checksum32(y, num) == ctx.checksum32(y2, num)
+    for m0 in sorted({0, 3839, 3840, num // 2, num - 4000}):
+        cnt = 2048
+        xs = synth.noise(cnt + T, first=m0)
+        want = ref.filter("filterAVXSymmetricRR", cnt, half, xs)
+        close(y.to_host(np.float32, cnt, offset_bytes=4 * m0), want)
+    for b_ in (x, y, y2):
+        b_.free()
+
+
+@pytest.mark.parametrize("T", [90, 31])
+@pytest.mark.parametrize("log2n", [18, 26])
+def test_stream_real_resampler_tuned_vs_generic_and_oracle(sdr, L, ctx, ref, T, log2n):
+    """cfg3 at full size: ring kernel == generic kernel bit for bit; windows vs the reference's resampleAVXRR"""
+    n = 1 << log2n
+    taps = synth.windowed_sinc_taps(T, 1 / 20, gain=3.0)
+    r = sdr.cudaResamplerR(3, 10, taps, sizeMultiple=8)
+    num = (n * 3 - r.numCoeffsR) // 10 + 1
+    x = ctx.alloc(4 * n + 64)
+    y = ctx.alloc(4 * num + 64)
+    y2 = ctx.alloc(4 * num + 64)
+    ctx.synth_noise(x, n)
+    L.check(L.lib.sdr_resample_stream(r.handle, x.ptr, n, y.ptr, num))
+    assert r.last_kernel().startswith("res_r_ring"), r.last_kernel()
+    ctx.synth_noise(x, n, first_float=0, offset_bytes=4)
+    # misaligned start: the tuned kernel only engages after a generic prefix reaches an aligned cycle boundary
+    L.check(L.lib.sdr_resample_stream(r.handle, x.at(4), n, y2.ptr, num))
+    assert ctx.checksum32(y, num) == ctx.checksum32(y2, num)
+    num_coeffs, increments, groups = op.prepare_coeffs(8, 3, 10, taps)
+    for k0 in sorted({0, 3 * 1000, 3 * (num // 6), 3 * ((num - 3000) // 3)}):
+        cnt = 1500
+        i0 = (k0 * 10 + 2) // 3
+        xs = synth.noise(cnt * 10 // 3 + 200, first=i0)
+        want, _ = ref.resample("resampleAVXRR", cnt, num_coeffs, 0, increments, groups, xs)
+        close(y.to_host(np.float32, cnt, offset_bytes=4 * k0), want)
+    for b_ in (x, y, y2):
+        b_.free()
+
+
 def test_sharded_plan_single_rank_equals_stream(sdr, L, ctx):
     """world = 1 plan through sdr_decimate_sharded == sdr_decimate_stream (no communicator needed)"""
     n = 1 << 20

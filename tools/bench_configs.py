@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Device-resident throughput of the non-headline BASELINE.json configs (measurement tool; prints one JSON line per
+config).  cfg1: 64-tap symmetric real filter; cfg3: 3/10 resampler, 90 taps, real; elementwise stages; cfg4 chain."""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+import sdr_b200  # noqa: E402
+import synth  # noqa: E402
+from sdr_b200 import _lib as L  # noqa: E402
+
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timed(ctx, fn, steps=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    ctx.sync()
+    e0, e1 = sdr_b200.Event(ctx), sdr_b200.Event(ctx)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    return e0.elapsed_ms(e1) / steps
+
+
+def main():
+    log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 27
+    n = 1 << log2n
+    ctx = sdr_b200.default_context()
+    x = ctx.alloc(8 * n + 256)
+    y = ctx.alloc(8 * n + 256)
+    ctx.synth_noise(x, 2 * n)
+    out = []
+
+    def report(name, ms, samples, bytes_per_sample, kernel=""):
+        gs = samples / (ms * 1e-3) / 1e9
+        out.append({"config": name, "ms": ms, "Gsamples_per_s": gs, "algo_GBps": gs * bytes_per_sample,
+                    "hbm_frac": gs * bytes_per_sample / PEAK, "samples": samples, "kernel": kernel})
+        print(json.dumps(out[-1]), flush=True)
+
+    # cfg1: fastFilterSymR, 64 taps (32 half taps), real
+    half = synth.windowed_sinc_taps(64, 1 / 4)[:32]
+    f = sdr_b200.cudaFilterSymR(half, ctx=ctx)
+    nr = 2 * n   # real samples available in the buffer
+    num = nr - 64 + 1
+    ms = timed(ctx, lambda: L.check(L.lib.sdr_filter_stream(f.handle, x.ptr, nr, y.ptr, num)))
+    report("cfg1 filter 64-tap sym real", ms, nr, 8.0)
+    # cfg3: fastResamplerR 3/10, 90 taps, real
+    t_res = synth.windowed_sinc_taps(90, 1 / 20, gain=3.0)
+    r = sdr_b200.cudaResamplerR(3, 10, t_res, ctx=ctx, sizeMultiple=8)
+    num = (nr * 3 - r.numCoeffsR) // 10 + 1
+    ms = timed(ctx, lambda: L.check(L.lib.sdr_resample_stream(r.handle, x.ptr, nr, y.ptr, num)))
+    report("cfg3 resample 3/10 90-tap real", ms, nr, 5.2)
+    # cfg2 for reference
+    taps = synth.windowed_sinc_taps(128, 1 / 16)
+    d = sdr_b200.cudaDecimatorC(8, taps, ctx=ctx, sizeMultiple=4)
+    num = (n - 128) // 8 + 1
+    ms = timed(ctx, lambda: L.check(L.lib.sdr_decimate_stream(d.handle, x.ptr, n, y.ptr, num)))
+    report("cfg2 decimate-by-8 128-tap complex", ms, n, 9.0, d.last_kernel())
+    # cfg4: the FM chain through connected device pipes, u8 IQ in
+    nb = n   # IQ pairs
+    raw = ctx.alloc(2 * nb)
+    ctx.synth_bytes(raw, 2 * nb)
+    fil = sdr_b200.cudaFilterSymR(half, ctx=ctx)
+
+    def chain():
+        p0 = sdr_b200.pipeConvertU8(ctx)
+        p1 = sdr_b200.pipeFirDecimator(d, 8192)
+        p2 = sdr_b200.pipeFmDemod(ctx)
+        p3 = sdr_b200.pipeFirResampler(r, 8192)
+        p4 = sdr_b200.pipeFirFilter(fil, 8192)
+        p5 = sdr_b200.pipeScale(0.2, ctx)
+        p0.connect(p1).connect(p2).connect(p3).connect(p4).connect(p5)
+        for p in (p1, p3, p4):
+            L.check(L.lib.sdr_pipe_set_batch(p.h, 1 << 22))
+        n_out = C.c_longlong()
+        chunk = 1 << 24   # bytes per push (device memory): 8M IQ pairs
+        L.check(L.lib.sdr_pipe_run(p0.h, p5.h, raw.ptr, chunk, (2 * nb) // chunk, L.SDR_DEVICE, y.ptr, 2 * n, L.SDR_DEVICE,
+                                   C.byref(n_out)))
+        for p in (p0, p1, p2, p3, p4, p5):
+            p.close()
+        return n_out.value
+    ms = timed(ctx, chain, steps=3, warmup=1)
+    report("cfg4 FM chain (u8 IQ -> audio), connected pipes, un-fused", ms, nb, 2.15)
+
+
+if __name__ == "__main__":
+    main()
