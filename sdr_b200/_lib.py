@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsdr_b200.so")
+LIB_PATH = os.environ.get("SDR_B200_LIB_PATH") or os.path.join(_HERE, "lib", "libsdr_b200.so")
 
 SDR_OK, SDR_EINVAL, SDR_EPRECOND, SDR_ECUDA, SDR_ENODEVICE, SDR_ENOMEM, SDR_ENCCL, SDR_EAGAIN = range(8)
 SDR_HOST, SDR_DEVICE, SDR_HOST_PINNED = 0, 1, 2

@@ -31,7 +31,9 @@ struct RingCfg {
     static constexpr int SLOT_BYTES = 32 * SEG_STRIDE;
     static constexpr int HALO_SEGS = (JB - 1 + R - 1) / R;  // segments of the NEXT sub-tile a pass reads
     static constexpr int NWARPS = 8;
-    static constexpr int NS = (220 * 1024 - HALO_SEGS * SEG_STRIDE - 256) / SLOT_BYTES;   // ring slots
+    static constexpr int NS_FIT = (220 * 1024 - HALO_SEGS * SEG_STRIDE - 256) / SLOT_BYTES;
+    static constexpr int NS = NS_FIT >= 2 * NWARPS ? 2 * NWARPS : NS_FIT;                  // ring slots
+    static constexpr bool GUARD = (NS % NWARPS) != 0;   // see slot_wait in ring_common.cuh
     static constexpr int RING_BYTES = NS * SLOT_BYTES + HALO_SEGS * SEG_STRIDE;           // + mirror of slot 0's head
     static constexpr int SMEM_BYTES = RING_BYTES + 2 * NS * 8 + NS * 4 + 256;
     static_assert(NS >= NWARPS + 3, "ring too small for 8 warps plus prefetch");
@@ -86,11 +88,9 @@ k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const floa
 
     for (int u = warp; u < cnt; u += C::NWARPS) {
         const int slot = u % C::NS, par = (u / C::NS) & 1;
-        const int slot2 = (u + 1) % C::NS, par2 = ((u + 1) / C::NS) & 1;
-        gen_wait(gen_armed + 4 * slot, u / C::NS + 1);
-        mbar_wait(bar_full + 8 * slot, par);
-        gen_wait(gen_armed + 4 * slot2, (u + 1) / C::NS + 1);
-        mbar_wait(bar_full + 8 * slot2, par2);
+        const int slot2 = (u + 1) % C::NS;
+        slot_wait<C::GUARD>(bar_full + 8 * slot, gen_armed + 4 * slot, u / C::NS + 1);
+        slot_wait<C::GUARD>(bar_full + 8 * slot2, gen_armed + 4 * slot2, (u + 1) / C::NS + 1);
 
         const unsigned char *base = smem + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE;
         u64 acc[R];
