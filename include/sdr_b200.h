@@ -251,6 +251,11 @@ int sdr_pipe_fir_filter(sdr_filter_t *f, int block_size_out, sdr_pipe_t **p);   
 int sdr_pipe_fir_decimator(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **p); /* firDecimator Filter.hs:574 */
 int sdr_pipe_fir_resampler(sdr_resampler_t *r, int block_size_out, sdr_pipe_t **p); /* firResampler Filter.hs:679 */
 int sdr_pipe_fm_demod(sdr_ctx_t *ctx, sdr_pipe_t **p);                              /* fmDemod      Demod.hs:40   */
+/* `P.map interleavedIQUnsignedByteToFloat >-> firDecimator d block_size_out >-> fmDemod` (fm.hs:34-37) as ONE fused
+ * stage: pushes are u8 IQ bytes (n = byte count, even), yields are vectors of block_size_out float phases.  Same
+ * stream, bit for bit, as the three stages connected one after the other. */
+int sdr_pipe_fm_frontend(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **p);
+const char *sdr_pipe_last_kernel(const sdr_pipe_t *p);
 int sdr_pipe_convert_u8(sdr_ctx_t *ctx, sdr_pipe_t **p); /* P.map interleavedIQUnsignedByteToFloat (Util.hs:104) */
 int sdr_pipe_scale(sdr_ctx_t *ctx, float factor, sdr_pipe_t **p);                   /* P.map (VG.map (* k)) fm.hs:40 */
 int sdr_pipe_destroy(sdr_pipe_t *p);

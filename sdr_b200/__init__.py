@@ -9,6 +9,6 @@ from .filter import (Decimator, Filter, NativePipe, Resampler, cudaDecimatorC, c
                      cudaFilterC, cudaFilterR, cudaFilterSymR, cudaResamplerC, cudaResamplerR, default_context,
                      firDecimator, firFilter, firResampler, pipeFirDecimator, pipeFirFilter, pipeFirResampler)
 from .util import (complexFloatToInterleavedIQSigned2048, dcBlocker, fmDemod, fmDemodVec,  # noqa: F401
-                   interleavedIQSigned2048ToFloat, interleavedIQUnsignedByteToFloat, pipeConvertU8, pipeFmDemod,
+                   interleavedIQSigned2048ToFloat, interleavedIQUnsignedByteToFloat, pipeConvertU8, pipeFmDemod, pipeFmFrontEnd,
                    pipeScale, scaleFast)
 from . import multigpu  # noqa: F401

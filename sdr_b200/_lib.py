@@ -134,6 +134,9 @@ _sig("sdr_pipe_fir_filter", _P, _I, c_void_pp)
 _sig("sdr_pipe_fir_decimator", _P, _I, c_void_pp)
 _sig("sdr_pipe_fir_resampler", _P, _I, c_void_pp)
 _sig("sdr_pipe_fm_demod", _P, c_void_pp)
+_sig("sdr_pipe_fm_frontend", _P, _I, c_void_pp)
+lib.sdr_pipe_last_kernel.restype = C.c_char_p
+lib.sdr_pipe_last_kernel.argtypes = [C.c_void_p]
 _sig("sdr_pipe_convert_u8", _P, c_void_pp)
 _sig("sdr_pipe_scale", _P, _F, c_void_pp)
 _sig("sdr_pipe_destroy", _P)

@@ -1,0 +1,233 @@
+// kernels_fm.cu -- fused front end of the FM receiver chain (cfg4, reference examples/fm/fm.hs:34-37):
+//
+//     P.map interleavedIQUnsignedByteToFloat >-> firDecimator deci >-> fmDemod
+//
+// as ONE persistent kernel: u8 IQ bytes in (2 B per sample instead of the 8 B of a float stream), float phase out
+// (4 B per D samples), nothing in between touches HBM.  Structure and inner product are those of k_dec_c_ring
+// (kernels_fast.cu); what changes:
+//   * the ring holds raw bytes: a sub-tile (256 outputs = 2048 samples) is 4 KB, staged by coalesced 16-byte cp.async
+//     (LDGSTS) into lane segments of 128 B padded to 144 B (odd number of 16-byte chunks: conflict-free LDS.128);
+//     completion through cp.async.mbarrier.arrive on the slot's barrier.  24 slots = 3 per warp, so every generation
+//     of a slot is consumed by the same warp and the parity wait needs no generation guard.
+//   * bytes become floats in registers: PRMT drops the byte into the mantissa of 2^23 (0x4B0000bb = 8388608 + b), one
+//     FFMA2 then computes (8388608 + b) * (1/128) - 65537 = (b - 128) / 128 for I and Q together -- exact, i.e.
+//     bit-identical to convertC (reference convert.c:15-20).
+//   * epilogue: phase(y[m] * conj(y[m-1])) per output (demod.cuh); y[m-1] of a lane's first output comes from the
+//     previous lane by shuffle; the first output of a sub-tile needs the last output of the previous sub-tile, which
+//     another warp computes at another time: every sub-tile therefore also stores its first and last COMPLEX output
+//     (16 B per 2048 samples) and k_fm_front_fixup patches the 1-in-256 outputs afterwards.
+// The FIR sum order is the same as everywhere else, so fused == un-fused bit for bit (tests/test_gpu_parity.py).
+// Roofline: 2 B in + 0.5 B out per sample make HBM irrelevant; the kernel is FP32-pipe bound (1024 + 184 FFMA2 per pass).
+#include "demod.cuh"
+#include "ring_common.cuh"
+
+namespace sdr {
+
+template <int T, int D, int R>
+struct FmCfg {
+    static_assert(T % D == 0 && D == 8 && R == 8, "one decimation block = 8 IQ pairs = one 16-byte chunk");
+    static constexpr int JB = T / D;
+    static constexpr int BLK_BYTES = D * 2;                 // 16
+    static constexpr int SEG_BYTES = R * BLK_BYTES;         // 128
+    static constexpr int SEG_STRIDE = SEG_BYTES + 16;       // 144 = 9 chunks (odd)
+    static constexpr int SUB_OUT = 32 * R;                  // 256 outputs
+    static constexpr int SUB_BYTES = 32 * SEG_BYTES;        // 4096 input bytes
+    static constexpr int SLOT_BYTES = 32 * SEG_STRIDE;      // 4608
+    static constexpr int HALO_SEGS = (JB - 1 + R - 1) / R;  // 2
+    static constexpr int NWARPS = 8;
+    static constexpr int NS = 24;
+    static constexpr int RING_BYTES = NS * SLOT_BYTES + HALO_SEGS * SEG_STRIDE;
+    static constexpr int BAR_OFFSET = ((RING_BYTES + 127) / 128) * 128;
+    static constexpr int SMEM_BYTES = BAR_OFFSET + 2 * NS * 8 + 128;
+    static_assert(NS % NWARPS == 0, "same-warp slot ownership (no generation guard)");
+};
+
+// 16-byte asynchronous copy; src_bytes = 0 zero-fills the destination without touching global memory
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// byte `idx` (0..3) of `word` -> float 8388608 + b
+__device__ __forceinline__ float byte_as_big_float(uint32_t word, int idx) {
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | (uint32_t)idx));
+}
+__device__ __forceinline__ u64 pack2f(float lo, float hi) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ float2 unpack2f(u64 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
+// bnd: 2 complex per sub-tile: [2t] = first output of sub-tile t, [2t+1] = last output.  The kernel covers ALL `num`
+// outputs: chunks past the end of the stream are zero-filled (no valid output needs them), stores of the ragged last
+// sub-tile are masked, and the stream's final complex output goes to *carry_out (the next call's carried sample).
+template <int T, int D, int R>
+__global__ void __launch_bounds__(256, 1)
+k_fm_front_ring(const uint8_t *__restrict__ in, long long n_chunks, float *__restrict__ out, long long num,
+                float2 *__restrict__ bnd, float2 *__restrict__ carry_out, const float *__restrict__ taps, long long n_sub) {
+    typedef FmCfg<T, D, R> C;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    long long q = n_sub / gridDim.x, rem = n_sub % gridDim.x;
+    long long s0 = blockIdx.x * q + (blockIdx.x < rem ? blockIdx.x : rem);
+    int cnt = (int)(q + (blockIdx.x < rem ? 1 : 0));
+    if (cnt == 0) return;
+
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t bar_full = ring + C::BAR_OFFSET;
+    const uint32_t bar_empty = bar_full + C::NS * 8;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::NS; s++) { mbar_init(bar_full + 8 * s, 32); mbar_init(bar_empty + 8 * s, 2); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // chunk c (16 B = 8 IQ pairs) of a sub-tile lands in segment c / 8 at offset (c % 8) * 16
+    auto issue_fill = [&](int u) {
+        const int slot = u % C::NS;
+        const int nchunk = (u == cnt) ? C::HALO_SEGS * R : 32 * R;   // halo-only fill: the first two segments
+        const long long chunk0 = (s0 + u) * (long long)(32 * R);
+        const unsigned char *src = in + chunk0 * 16;
+        const uint32_t dst = ring + slot * C::SLOT_BYTES;
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            const int c = i * 32 + lane;
+            if (c < nchunk) {
+                const bool ok = chunk0 + c < n_chunks;
+                cp_async16(dst + (c >> 3) * C::SEG_STRIDE + (c & 7) * 16, ok ? src + c * 16 : in, ok ? 16u : 0u);
+            }
+        }
+        if (slot == 0 && lane < C::HALO_SEGS * R) {   // mirror of slot 0's head behind the last slot
+            const bool ok = chunk0 + lane < n_chunks;
+            cp_async16(ring + C::NS * C::SLOT_BYTES + (lane >> 3) * C::SEG_STRIDE + (lane & 7) * 16, ok ? src + lane * 16 : in,
+                       ok ? 16u : 0u);
+        }
+        cp_async_arrive(bar_full + 8 * slot);
+    };
+
+    for (int u = warp; u < C::NS && u <= cnt; u += C::NWARPS) issue_fill(u);
+
+    float tap[T];
+#pragma unroll
+    for (int k = 0; k < T; k++) tap[k] = __ldg(taps + k);
+    const u64 k_scale = dup2(0.0078125f), k_bias = dup2(-65537.0f);
+
+    for (int u = warp; u < cnt; u += C::NWARPS) {
+        const int slot = u % C::NS, slot2 = (u + 1) % C::NS;
+        mbar_wait(bar_full + 8 * slot, (u / C::NS) & 1);
+        mbar_wait(bar_full + 8 * slot2, ((u + 1) / C::NS) & 1);
+
+        const unsigned char *base = smem + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE;
+        u64 acc[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = 0ULL;
+#pragma unroll
+        for (int b = 0; b < R + C::JB - 1; b++) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(base + (b / R) * C::SEG_STRIDE + (b % R) * C::BLK_BYTES);
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+            u64 v[D];
+#pragma unroll
+            for (int p = 0; p < D; p++) {   // sample p: bytes (2p, 2p+1) of the chunk = (I, Q)
+                const uint32_t word = w[p >> 1];
+                const int b0 = (p & 1) * 2;
+                v[p] = ffma2(pack2f(byte_as_big_float(word, b0), byte_as_big_float(word, b0 + 1)), k_scale, k_bias);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int j = b - r;
+                if (j < 0 || j >= C::JB) continue;
+#pragma unroll
+                for (int p = 0; p < D; p++) acc[r] = ffma2(v[p], dup2(tap[j * D + p]), acc[r]);
+            }
+        }
+        // the slot's bytes are in registers: hand it back before the (long) epilogue
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bar_empty + 8 * slot);
+            if (u == 0) mbar_arrive(bar_empty + 8 * slot);
+            mbar_arrive(bar_empty + 8 * slot2);
+        }
+        if (u + C::NS <= cnt) {
+            mbar_wait(bar_empty + 8 * slot, (u / C::NS) & 1);
+            issue_fill(u + C::NS);
+        }
+
+        // epilogue: FM discriminator
+        float2 y[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) y[r] = unpack2f(acc[r]);
+        float2 prev;
+        prev.x = __shfl_up_sync(0xffffffffu, y[R - 1].x, 1);
+        prev.y = __shfl_up_sync(0xffffffffu, y[R - 1].y, 1);
+        float ph[R];
+        ph[0] = fm_phase(y[0], prev);   // lane 0's value is meaningless here: patched by k_fm_front_fixup
+#pragma unroll
+        for (int r = 1; r < R; r++) ph[r] = fm_phase(y[r], y[r - 1]);
+        const long long m0 = (s0 + u) * (long long)C::SUB_OUT + lane * R;   // this lane's first output index
+        float *os = out + m0;
+        if (vec_store && m0 + R <= num) {
+            float4 *o = reinterpret_cast<float4 *>(os);
+#pragma unroll
+            for (int r = 0; r < R; r += 4) o[r / 4] = make_float4(ph[r], ph[r + 1], ph[r + 2], ph[r + 3]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) if (m0 + r < num) os[r] = ph[r];
+        }
+        if (lane == 0) bnd[2 * (s0 + u)] = y[0];
+        if (lane == 31) bnd[2 * (s0 + u) + 1] = y[R - 1];
+#pragma unroll
+        for (int r = 0; r < R; r++) if (m0 + r == num - 1) *carry_out = y[r];
+    }
+}
+
+// out[256 t] = phase(first[t] * conj(last[t-1])); sub-tile 0 uses the carried sample *carry
+__global__ void __launch_bounds__(256) k_fm_front_fixup(float *__restrict__ out, const float2 *__restrict__ bnd,
+                                                        const float2 *__restrict__ carry, long long n_sub, int sub_out) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_sub; t += (long long)gridDim.x * blockDim.x) {
+        const float2 prev = (t == 0) ? *carry : bnd[2 * (t - 1) + 1];
+        out[t * sub_out] = fm_phase(bnd[2 * t], prev);
+    }
+}
+
+// Fused convert + decimate + demod of outputs [0, num) of a byte stream holding n_samples IQ pairs.  d_carry: previous
+// stream sample (re, im) on the device, read by the fix-up; d_carry_out receives the last decimated complex output;
+// d_bnd: scratch of 2 complex per sub-tile (ceil(num / 256) sub-tiles).  *done = num when the shape has a tuned kernel.
+int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, const uint8_t *d_in, long long n_samples, float *d_out,
+                    long long num, float2 *d_bnd, long long bnd_capacity_subtiles, const float2 *d_carry, float2 *d_carry_out,
+                    long long *done, const char **name) {
+    *done = 0;
+    *name = "unfused";
+    if (T != 128 || D != 8 || num <= 0) return SDR_OK;
+    if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 3) != 0) return SDR_OK;
+    typedef FmCfg<128, 8, 8> C;
+    if ((num - 1) * D + T > n_samples) return set_error(SDR_EINVAL, "launch_fm_front: %lld outputs need more than %lld samples", num, n_samples);
+    long long n_sub = (num + C::SUB_OUT - 1) / C::SUB_OUT;
+    if (bnd_capacity_subtiles < n_sub) return set_error(SDR_EINVAL, "launch_fm_front: boundary scratch too small");
+    SDR_TRY(c->bind());
+    static thread_local int attr_dev = -1;
+    if (attr_dev != c->device) {
+        SDR_CUDA(cudaFuncSetAttribute(k_fm_front_ring<128, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_dev = c->device;
+    }
+    int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
+    k_fm_front_ring<128, 8, 8><<<grid, 256, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
+    c->launches++;
+    SDR_CUDA(cudaGetLastError());
+    long long fg = (n_sub + 255) / 256;
+    if (fg > 4LL * c->sm_count) fg = 4LL * c->sm_count;
+    k_fm_front_fixup<<<(int)fg, 256, 0, c->s()>>>(d_out, d_bnd, d_carry, n_sub, C::SUB_OUT);
+    c->launches++;
+    SDR_CUDA(cudaGetLastError());
+    *done = num;
+    *name = "fm_front_ring<128,8,8>";
+    return SDR_OK;
+}
+
+}  // namespace sdr

@@ -12,6 +12,7 @@
 //   fm demod          phase(s[n] * conj(s[n-1]))                         Demod.hs:21-36
 //   dc blocker        y[n] = x[n] - x[n-1] + 0.997 y[n-1]                filter.c:152-161
 #include "common.cuh"
+#include "demod.cuh"
 
 #include <cstdlib>
 #include <type_traits>
@@ -379,31 +380,12 @@ int launch_scale(Ctx *c, float k, const float *d_in, float *d_out, long long n) 
     return SDR_OK;
 }
 
-// GHC's class-default atan2 for Float (GHC.Float), built on atan: see oracle/sdr_oracle.c hs_atan2f
-__device__ __forceinline__ bool neg_zero(float v) { return v == 0.0f && signbit(v); }
-__device__ float hs_atan2f_dev(float y, float x) {
-    const float pi = 3.14159265358979323846f;
-    bool flip = (x <= 0 && y < 0) || (x < 0 && neg_zero(y)) || (neg_zero(x) && neg_zero(y));
-    if (flip) y = -y;   // the reference recurses once with -y and negates the result
-    float r;
-    if (x > 0) r = atanf(__fdiv_rn(y, x));
-    else if (x == 0 && y > 0) r = pi / 2;
-    else if (x < 0 && y > 0) r = __fadd_rn(pi, atanf(__fdiv_rn(y, x)));
-    else if (y == 0 && (x < 0 || neg_zero(x))) r = pi;
-    else if (x == 0 && y == 0) r = y;
-    else r = x + y;
-    return flip ? -r : r;
-}
-
 __global__ void __launch_bounds__(256) k_fm_demod(float last_re, float last_im, const float2 *__restrict__ last_ptr,
                                                   const float2 *__restrict__ in, float *__restrict__ out, long long n) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float2 s = __ldg(in + i);
         float2 l = (i == 0) ? (last_ptr ? *last_ptr : make_float2(last_re, last_im)) : __ldg(in + i - 1);
-        float nli = -l.y;
-        float re = __fsub_rn(__fmul_rn(s.x, l.x), __fmul_rn(s.y, nli));
-        float im = __fadd_rn(__fmul_rn(s.x, nli), __fmul_rn(s.y, l.x));
-        out[i] = (re == 0.0f && im == 0.0f) ? 0.0f : hs_atan2f_dev(im, re);
+        out[i] = fm_phase(s, l);
     }
 }
 int launch_fm_demod(Ctx *c, float last_re, float last_im, const float *d_in, float *d_out, long long n) {

@@ -37,6 +37,7 @@ template <int T, int R, int S>
 __global__ void __launch_bounds__(256, 1)
 k_fir_r_ring(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ taps, long long n_slots) {
     typedef FirRCfg<T, R, S> C;
+    const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long q = n_slots / gridDim.x, rem = n_slots % gridDim.x;
@@ -75,9 +76,15 @@ k_fir_r_ring(const float *__restrict__ in, float *__restrict__ out, const float 
                     }
                 }
             }
-            float4 *o = reinterpret_cast<float4 *>(out_slot + (p * 32 + lane) * R);
+            float *os = out_slot + (p * 32 + lane) * R;
+            if (vec_store) {
+                float4 *o = reinterpret_cast<float4 *>(os);
 #pragma unroll
-            for (int r = 0; r < R; r += 4) o[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
+                for (int r = 0; r < R; r += 4) o[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
+            } else {   // output not 16-byte aligned (a pipe's FIFO cursor): scalar stores, L2 merges the sectors
+#pragma unroll
+                for (int r = 0; r < R; r++) os[r] = acc[r];
+            }
         }
         ring.release_and_refill(u, lane);
     }
@@ -111,7 +118,7 @@ int launch_fir_r_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_
                       long long num, long long *done, const char **name) {
     *done = 0;
     *name = "fir_tile";
-    if (D != 1 || (((uintptr_t)d_in | (uintptr_t)d_out) & 15) != 0) return SDR_OK;
+    if (D != 1 || (((uintptr_t)d_in) & 15) != 0) return SDR_OK;   // TMA needs a 16-byte aligned source; any output alignment
     if (T == 64) { *name = "fir_r_ring<64,20,6>"; return launch_fir_r<64, 20, 6>(c, d_taps, d_in, n_in, d_out, num, done); }
     if (T == 32) { *name = "fir_r_ring<32,20,6>"; return launch_fir_r<32, 20, 6>(c, d_taps, d_in, n_in, d_out, num, done); }
     if (T == 128) { *name = "fir_r_ring<128,20,6>"; return launch_fir_r<128, 20, 6>(c, d_taps, d_in, n_in, d_out, num, done); }
@@ -155,6 +162,7 @@ template <int L, int M, int T, int CY, int S>
 __global__ void __launch_bounds__(256, 1)
 k_res_r_ring(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ taps, long long n_slots) {
     typedef ResRCfg<L, M, T, CY, S> C;
+    const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 7) == 0;
     typedef Phase<L, M, T> P;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -197,9 +205,15 @@ k_res_r_ring(const float *__restrict__ in, float *__restrict__ out, const float 
                     }
                 }
             }
-            float2 *o2 = reinterpret_cast<float2 *>(out_slot + (p * 32 + lane) * C::LANE_OUT);
+            float *os = out_slot + (p * 32 + lane) * C::LANE_OUT;
+            if (vec_store) {
+                float2 *o2 = reinterpret_cast<float2 *>(os);
 #pragma unroll
-            for (int o = 0; o < C::LANE_OUT; o += 2) o2[o / 2] = make_float2(acc[o], acc[o + 1]);
+                for (int o = 0; o < C::LANE_OUT; o += 2) o2[o / 2] = make_float2(acc[o], acc[o + 1]);
+            } else {
+#pragma unroll
+                for (int o = 0; o < C::LANE_OUT; o++) os[o] = acc[o];
+            }
         }
         ring.release_and_refill(u, lane);
     }
@@ -234,7 +248,7 @@ int launch_res_r_fast(Ctx *c, int L, int M, int n_taps, const float *d_plain_tap
                       float *d_out, long long num, long long *done, const char **name) {
     *done = 0;
     *name = "fir_tile";
-    if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 7) != 0) return SDR_OK;
+    if ((((uintptr_t)d_in) & 15) != 0) return SDR_OK;
     if (L == 3 && M == 10 && n_taps == 90) {
         *name = "res_r_ring<3,10,90,6,2>";
         return launch_res_r<3, 10, 90, 6, 2>(c, d_plain_taps, d_in, n_in, d_out, num, done);

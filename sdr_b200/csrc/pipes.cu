@@ -12,6 +12,9 @@
 // Outputs are re-blocked into vectors of exactly block_size_out elements like advanceOutBuf (Filter.hs:516-523).
 #include "records.cuh"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <deque>
 
 namespace sdr {
@@ -40,10 +43,58 @@ struct LinBuf {
         return SDR_OK;
     }
     void consume(size_t bytes) { rd += bytes; if (rd == wr) rd = wr = 0; }
+    // move the (small) live region so that it starts `lead` bytes past a 16-byte boundary at the front of the buffer;
+    // skipped when source and destination would overlap
+    int realign(size_t lead) {
+        size_t live = size();
+        if (rd == lead) return SDR_OK;
+        if (lead + live > rd || lead + live > cap) return SDR_OK;
+        if (live) SDR_CUDA(cudaMemcpyAsync(p + lead, p + rd, live, cudaMemcpyDeviceToDevice, c->stream));
+        rd = lead; wr = lead + live;
+        return SDR_OK;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = rd = wr = 0; }
 };
 
-enum { P_FILTER, P_DECIM, P_RESAMP, P_FMDEMOD, P_CONVERT, P_SCALE };
+// Tracing aid.  SDR_B200_TRACE=1: synchronise around every stage step and print its wall time (serialises the stream).
+// SDR_B200_TRACE=2: record CUDA events around every step without synchronising, print device-side durations and
+// host-side issue times at the next sdr_pipe_sync.
+static int trace_mode() { static const int m = getenv("SDR_B200_TRACE") ? atoi(getenv("SDR_B200_TRACE")) : 0; return m; }
+struct TraceRec { const char *label; long long n; cudaEvent_t e0, e1; double host_us; };
+static std::deque<TraceRec> &trace_log() { static std::deque<TraceRec> q; return q; }
+struct TraceScope {
+    const char *label; Ctx *c; long long n; std::chrono::steady_clock::time_point t0; cudaEvent_t e0 = nullptr;
+    TraceScope(const char *l, Ctx *ctx, long long count) : label(l), c(ctx), n(count) {
+        if (!trace_mode()) return;
+        if (trace_mode() == 1) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->side); }
+        else { cudaEventCreate(&e0); cudaEventRecord(e0, c->stream); }
+        t0 = std::chrono::steady_clock::now();
+    }
+    ~TraceScope() {
+        if (!trace_mode()) return;
+        if (trace_mode() == 1) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->side); }
+        double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        if (trace_mode() == 1) { fprintf(stderr, "[sdr_b200 trace] %-18s n=%-10lld %9.1f us\n", label, n, us); return; }
+        cudaEvent_t e1; cudaEventCreate(&e1); cudaEventRecord(e1, c->stream);
+        trace_log().push_back({label, n, e0, e1, us});
+    }
+};
+static void trace_dump() {
+    if (trace_mode() != 2) return;
+    cudaEvent_t first = trace_log().empty() ? nullptr : trace_log().front().e0;
+    for (auto &r : trace_log()) {
+        float ms = 0, at = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        cudaEventElapsedTime(&at, first, r.e0);
+        fprintf(stderr, "[sdr_b200 trace] %-18s n=%-10lld device %9.1f us (starts at %9.1f us)  host issue %8.1f us\n", r.label, r.n,
+                ms * 1e3, at * 1e3, r.host_us);
+    }
+    for (auto &r : trace_log()) { if (r.e0 != first) cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    if (first) cudaEventDestroy(first);
+    trace_log().clear();
+}
+
+enum { P_FILTER, P_DECIM, P_RESAMP, P_FMDEMOD, P_CONVERT, P_SCALE, P_FMFRONT };
 
 }  // namespace sdr
 
@@ -65,6 +116,10 @@ struct sdr_pipe {
     long long n_total = 0;            // input elements pushed so far
     float scale_k = 1.0f;
     float *d_last = nullptr;          // fmDemod: previous sample (re, im), starts at 0 (Demod.hs:41)
+    // fused FM front end: per-sub-tile boundary samples and scratch for the un-fused prefix / ragged end
+    LinBuf bnd, scratch_x, scratch_y;
+    int last_sel = 0;                 // which half of the double-buffered carried sample is current
+    const char *last_kernel = "none";
     sdr_pipe *downstream = nullptr;
     const char *assert_name = "";
     // SDR_HOST_PINNED pushes: host-to-device copies of vectors that are contiguous on both sides are merged and
@@ -77,7 +132,7 @@ struct sdr_pipe {
 
 namespace sdr {
 
-static bool is_fir_kind(int k) { return k == P_FILTER || k == P_DECIM || k == P_RESAMP; }
+static bool is_fir_kind(int k) { return k == P_FILTER || k == P_DECIM || k == P_RESAMP || k == P_FMFRONT; }
 
 static int flush_pending(sdr_pipe *p) {
     if (p->pend_bytes) {
@@ -88,6 +143,7 @@ static int flush_pending(sdr_pipe *p) {
 }
 
 static int pipe_push_dev(sdr_pipe *p, const void *d_src, long long n);
+static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, long long n_vecs = 1);
 
 // hand everything that is complete to the connected stage (device to device, stream ordered)
 static int forward(sdr_pipe *p) {
@@ -99,14 +155,27 @@ static int forward(sdr_pipe *p) {
             // a FIR stage only sees the flat stream: hand it all complete vectors as one contiguous push
             SDR_TRY(pipe_push_dev(p->downstream, p->fifo.p + p->fifo.rd, nb * p->block_out));
             p->fifo.consume((size_t)(nb * p->block_out) * p->out_eb);
-        } else {
-            // element-wise stages yield one vector per awaited vector: keep the vector structure
-            for (long long b = 0; b < nb; b++) {
-                SDR_TRY(pipe_push_dev(p->downstream, p->fifo.p + p->fifo.rd, p->block_out));
-                p->fifo.consume((size_t)p->block_out * p->out_eb);
-            }
+        } else if (nb > 0) {
+            // element-wise stages yield one vector per awaited vector: one launch over all of them, but the vector
+            // structure (nb vectors of block_out elements) is kept in the stage's queue
+            SDR_TRY(pipe_push_any(p->downstream, p->fifo.p + p->fifo.rd, nb * p->block_out, SDR_DEVICE, nb));
+            p->fifo.consume((size_t)(nb * p->block_out) * p->out_eb);
         }
     } else {
+        if (is_fir_kind(p->downstream->kind) && p->vec_lens.size() > 1) {
+            // a FIR stage only sees the flat stream: hand it all queued vectors as one contiguous push (each must
+            // still satisfy the stage's minimum-length precondition, checked on the shortest)
+            long long total = 0, shortest = p->vec_lens.front();
+            for (long long n : p->vec_lens) { total += n; if (n < shortest) shortest = n; }
+            sdr_pipe *d = p->downstream;
+            long long need = (d->kind == P_RESAMP) ? (d->res->T + d->res->L - 1) / d->res->L : d->fir->T;
+            if (shortest >= need) {
+                p->vec_lens.clear();
+                SDR_TRY(pipe_push_dev(d, p->fifo.p + p->fifo.rd, total));
+                p->fifo.consume((size_t)total * p->out_eb);
+                return SDR_OK;
+            }
+        }
         while (!p->vec_lens.empty()) {
             long long n = p->vec_lens.front();
             p->vec_lens.pop_front();
@@ -114,6 +183,57 @@ static int forward(sdr_pipe *p) {
             p->fifo.consume((size_t)n * p->out_eb);
         }
     }
+    return SDR_OK;
+}
+
+// un-fused convert -> decimate -> demod of outputs [first, first + n) of the resident byte stream; `slot` selects one
+// of two scratch regions so the complex outputs of an earlier call stay readable.  *last = its final complex output.
+static int fm_unfused(sdr_pipe *p, long long first, long long n, const float *d_carry, float *d_out, int slot,
+                      const float **last) {
+    FirRec &f = *p->fir;
+    const long long n_s = (n - 1) * f.D + f.T;
+    // region 0 (the <= 3-output alignment prefix) is a fixed 4 KB, region 1 (the ragged end) follows it
+    const size_t xo = slot ? 4096 : 0, yo = slot ? 4096 : 0;
+    p->scratch_x.rd = p->scratch_x.wr = 0; p->scratch_y.rd = p->scratch_y.wr = 0;
+    SDR_TRY(p->scratch_x.reserve(4096 + (size_t)n_s * 8 + 256));
+    SDR_TRY(p->scratch_y.reserve(4096 + (size_t)n * 8 + 256));
+    float *x = (float *)(p->scratch_x.p + xo), *y = (float *)(p->scratch_y.p + yo);
+    SDR_TRY(launch_convert_u8(p->ctx, (const uint8_t *)(p->in.p + p->in.rd) + 2 * first * f.D, x, 2 * n_s));
+    Seg2 seg = {x, n_s, nullptr, 0};
+    SDR_TRY(f.run(seg, 0, y, n, false));
+    SDR_TRY(launch_fm_demod_carry(p->ctx, d_carry, y, d_out, n));
+    *last = y + 2 * (n - 1);
+    return SDR_OK;
+}
+
+// P.map convert >-> firDecimator >-> fmDemod as one stage.  The fused kernel covers every output (ragged last
+// sub-tile and unaligned FIFO cursor included); shapes without a tuned kernel run the three stages un-fused.
+static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
+    FirRec &f = *p->fir;
+    const long long have = (long long)(p->in.size() / 2);   // IQ pairs resident
+    long long count = (have >= f.T) ? (have - f.T) / f.D + 1 : 0;
+    if (!(count > 0 && fifo_have + count >= p->block_out && fifo_have + count >= batch)) return SDR_OK;
+    SDR_TRY(flush_pending(p));
+    TraceScope tr("fm_front", p->ctx, count);
+    SDR_TRY(p->fifo.reserve((size_t)count * 4));
+    float *out = (float *)(p->fifo.p + p->fifo.wr);
+    p->bnd.rd = p->bnd.wr = 0;
+    SDR_TRY(p->bnd.reserve((size_t)(count / 256 + 2) * 16));
+    // the carried sample is double buffered: the fix-up reads the old one while the kernel writes the new one
+    float *carry_in = p->d_last + 2 * p->last_sel, *carry_out = p->d_last + 2 * (p->last_sel ^ 1);
+    long long done = 0;
+    const char *name = nullptr;
+    SDR_TRY(launch_fm_front(p->ctx, f.T, f.D, f.d_taps, (const uint8_t *)(p->in.p + p->in.rd), have, out, count, (float2 *)p->bnd.p,
+                            (long long)(p->bnd.cap / 16), (const float2 *)carry_in, (float2 *)carry_out, &done, &name));
+    p->last_kernel = name;
+    if (done < count) {
+        const float *last = nullptr;
+        SDR_TRY(fm_unfused(p, 0, count, carry_in, out, 1, &last));
+        SDR_CUDA(cudaMemcpyAsync(carry_out, last, 8, cudaMemcpyDeviceToDevice, p->ctx->stream));
+    }
+    p->last_sel ^= 1;
+    p->fifo.wr += (size_t)count * 4;
+    p->in.rd += (size_t)(count * f.D) * 2;
     return SDR_OK;
 }
 
@@ -130,6 +250,7 @@ static int process_fir(sdr_pipe *p, bool force = false) {
         // invisible to the caller because vectors are only ever yielded whole)
         if (count > 0 && fifo_have + count >= p->block_out && (fifo_have + count >= batch)) {
             SDR_TRY(flush_pending(p));
+            TraceScope tr("resampler", p->ctx, count);
             long long i_k = (p->k_next * r.M + r.L - 1) / r.L;   // ceil(k M / L): first sample of output k
             SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
             Seg2 seg = {p->in.p + p->in.rd, have, nullptr, 0};
@@ -138,20 +259,30 @@ static int process_fir(sdr_pipe *p, bool force = false) {
             p->k_next = total_out;
             long long new_pos = (p->k_next * r.M + r.L - 1) / r.L;
             if (new_pos > p->n_total) new_pos = p->n_total;
-            p->in.rd += (size_t)(new_pos - p->pos) * p->in_eb;   // the tail stays in place: no copy
+            p->in.rd += (size_t)(new_pos - p->pos) * p->in_eb;
             p->pos = new_pos;
+            if (!r.cplx && p->in.size() <= (1u << 16)) {
+                // the tuned kernel starts at the next cycle boundary (output index multiple of ng) with a 16-byte
+                // aligned window: park the short tail so that this start lands on a 16-byte boundary
+                long long kb = ((p->k_next + r.ng - 1) / r.ng) * r.ng;
+                long long s0 = (kb * r.M + r.L - 1) / r.L - p->pos;   // floats from the tail start to that window
+                SDR_TRY(p->in.realign((size_t)((4 - (s0 & 3)) & 3) * 4));
+            }
         }
         return SDR_OK;
     }
+    if (p->kind == P_FMFRONT) return process_fm_front(p, fifo_have, batch);
     FirRec &f = *p->fir;
     long long count = (have >= f.T) ? (have - f.T) / f.D + 1 : 0;
     if (count > 0 && fifo_have + count >= p->block_out && (fifo_have + count >= batch)) {
         SDR_TRY(flush_pending(p));
+        TraceScope tr(p->kind == P_FILTER ? "filter" : "decimator", p->ctx, count);
         SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
         Seg2 seg = {p->in.p + p->in.rd, have, nullptr, 0};
         SDR_TRY(f.run(seg, 0, p->fifo.p + p->fifo.wr, count, false));
         p->fifo.wr += (size_t)count * p->out_eb;
         p->in.rd += (size_t)(count * f.D) * p->in_eb;
+        if ((p->in.rd & 15) && p->in.size() <= (1u << 16)) SDR_TRY(p->in.realign(0));   // keep the tuned kernels' 16-byte alignment
     }
     return SDR_OK;
 }
@@ -180,11 +311,16 @@ static int fetch(sdr_pipe *p, void *d_dst, const void *src, size_t bytes, int me
     return SDR_OK;
 }
 
-static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem) {
+static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, long long n_vecs) {
     SDR_TRY(p->ctx->bind());
+    TraceScope tr_push("push(total)", p->ctx, n);
     if (is_fir_kind(p->kind)) {
         // the reference asserts every awaited vector holds at least numCoeffs samples (Filter.hs:544,586,691)
         long long need = (p->kind == P_RESAMP) ? (p->res->T + p->res->L - 1) / p->res->L : p->fir->T;
+        if (p->kind == P_FMFRONT) {
+            if (n & 1) return set_error(SDR_EINVAL, "FM front end: odd byte count %lld (interleaved I/Q pairs expected)", n);
+            need *= 2;
+        }
         if (n < need) return set_error(SDR_EPRECOND, "%s 1: input vector of %lld elements is shorter than numCoeffs (%lld)",
                                        p->assert_name, n, need);
         if (p->in.wr + (size_t)n * p->in_eb > p->in.cap) SDR_TRY(flush_pending(p));   // the buffer is about to move
@@ -217,7 +353,7 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem) {
         if (n) SDR_CUDA(cudaMemcpyAsync(p->d_last, (const char *)d_src + (size_t)(n - 1) * 8, 8, cudaMemcpyDeviceToDevice, p->ctx->stream));
     }
     p->fifo.wr += (size_t)n_out * p->out_eb;
-    p->vec_lens.push_back(n_out);
+    for (long long v = 0; v < n_vecs; v++) p->vec_lens.push_back(n_out / n_vecs);   // n_vecs equal vectors in one launch
     return forward(p);
 }
 
@@ -258,6 +394,19 @@ int sdr_pipe_fir_resampler(sdr_resampler_t *r, int block_size_out, sdr_pipe_t **
     p->res = &r->r; p->in_eb = p->out_eb = elem_bytes(r->r.cplx); p->block_out = block_size_out; p->assert_name = "resample";
     return SDR_OK;
 }
+int sdr_pipe_fm_frontend(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **out) {
+    if (!d || block_size_out <= 0) return set_error(SDR_EINVAL, "sdr_pipe_fm_frontend: bad argument");
+    if (!d->r.cplx) return set_error(SDR_EINVAL, "sdr_pipe_fm_frontend: the decimator must be a complex-data one (fastDecimatorC)");
+    sdr_pipe *p;
+    SDR_TRY(new_pipe(d->r.ctx, P_FMFRONT, out, &p));
+    p->fir = &d->r; p->in_eb = 1; p->out_eb = 4; p->block_out = block_size_out; p->assert_name = "decimate";
+    p->bnd.c = p->scratch_x.c = p->scratch_y.c = p->ctx;
+    SDR_CUDA(cudaMalloc(&p->d_last, 16));
+    SDR_CUDA(cudaMemsetAsync(p->d_last, 0, 16, p->ctx->stream));
+    return SDR_OK;
+}
+const char *sdr_pipe_last_kernel(const sdr_pipe_t *p) { return p ? p->last_kernel : "none"; }
+
 int sdr_pipe_fm_demod(sdr_ctx_t *ctx, sdr_pipe_t **out) {
     sdr_pipe *p;
     SDR_TRY(new_pipe(reinterpret_cast<Ctx *>(ctx), P_FMDEMOD, out, &p));
@@ -282,7 +431,7 @@ int sdr_pipe_destroy(sdr_pipe_t *p) {
     if (!p) return SDR_OK;
     p->ctx->bind();
     cudaStreamSynchronize(p->ctx->stream);
-    p->in.release(); p->fifo.release();
+    p->in.release(); p->fifo.release(); p->bnd.release(); p->scratch_x.release(); p->scratch_y.release();
     if (p->d_last) cudaFree(p->d_last);
     delete p;
     return SDR_OK;
@@ -341,6 +490,7 @@ int sdr_pipe_sync(sdr_pipe_t *p) {
     SDR_TRY(p->ctx->bind());
     SDR_TRY(flush_pending(p));
     SDR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    trace_dump();
     return SDR_OK;
 }
 
@@ -350,7 +500,8 @@ int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs) {
     if (is_fir_kind(p->kind) && min_outputs > 0) {
         // size both buffers for the batch once, instead of growing by doubling while the stream runs
         SDR_TRY(p->ctx->bind());
-        long long in_per_out = (p->kind == P_RESAMP) ? (p->res->M + p->res->L - 1) / p->res->L : p->fir->D;
+        long long in_per_out = (p->kind == P_RESAMP) ? (p->res->M + p->res->L - 1) / p->res->L
+                             : (p->kind == P_FMFRONT) ? 2 * p->fir->D : p->fir->D;
         long long taps = (p->kind == P_RESAMP) ? p->res->T : p->fir->T;
         SDR_TRY(p->in.reserve((size_t)(2 * (min_outputs + p->block_out) * in_per_out + taps) * p->in_eb));
         SDR_TRY(p->fifo.reserve((size_t)(2 * (min_outputs + p->block_out)) * p->out_eb));
@@ -372,13 +523,17 @@ static int drain(sdr_pipe *sink, void *out, long long out_capacity, int out_mem,
         *written += n;
         return SDR_OK;
     }
-    while (!sink->vec_lens.empty()) {
-        if (*written + sink->vec_lens.front() > out_capacity)
-            return set_error(SDR_EINVAL, "sdr_pipe_run: output capacity %lld too small", out_capacity);
-        long long got = 0;
-        SDR_TRY(sdr_pipe_pop(sink, (char *)out + (size_t)*written * sink->out_eb, &got, out_mem));
-        *written += got;
-    }
+    // element-wise stage: the queued vectors are contiguous in the FIFO and are written back to back anyway
+    long long total = 0;
+    for (long long n : sink->vec_lens) total += n;
+    if (total == 0) { sink->vec_lens.clear(); return SDR_OK; }
+    if (*written + total > out_capacity) return set_error(SDR_EINVAL, "sdr_pipe_run: output capacity %lld too small", out_capacity);
+    SDR_CUDA(cudaMemcpyAsync((char *)out + (size_t)*written * sink->out_eb, sink->fifo.p + sink->fifo.rd, (size_t)total * sink->out_eb,
+                             out_mem == SDR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sink->ctx->stream));
+    if (out_mem == SDR_HOST) SDR_CUDA(cudaStreamSynchronize(sink->ctx->stream));
+    sink->fifo.consume((size_t)total * sink->out_eb);
+    sink->vec_lens.clear();
+    *written += total;
     return SDR_OK;
 }
 
@@ -390,6 +545,7 @@ int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_
         return set_error(SDR_EINVAL, "sdr_pipe_run: bad argument");
     long long written = 0;
     SDR_TRY(p->ctx->bind());
+    auto t_start = std::chrono::steady_clock::now();
     for (long long v = 0; v < n_vecs; v++) {
         SDR_TRY(pipe_push_any(p, (const char *)in + (size_t)(v * vec_len) * p->in_eb, vec_len, in_mem));
         SDR_TRY(drain(sink, out, out_capacity, out_mem, &written));
@@ -400,7 +556,12 @@ int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_
         if (q == sink) break;
     }
     SDR_TRY(drain(sink, out, out_capacity, out_mem, &written));
+    auto t_issued = std::chrono::steady_clock::now();
     SDR_TRY(sdr_pipe_sync(p));
+    if (trace_mode())
+        fprintf(stderr, "[sdr_b200 trace] sdr_pipe_run: host issue %.1f us, final sync %.1f us\n",
+                std::chrono::duration<double, std::micro>(t_issued - t_start).count(),
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_issued).count());
     *n_out = written;
     return SDR_OK;
 }

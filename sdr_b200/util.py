@@ -82,6 +82,14 @@ def pipeScale(factor, ctx=None) -> NativePipe:
     return NativePipe(h, ctx, np.float32, np.float32)
 
 
+def pipeFmFrontEnd(decimator, blockSizeOut) -> NativePipe:
+    """P.map interleavedIQUnsignedByteToFloat >-> firDecimator decimator blockSizeOut >-> fmDemod  (fm.hs:34-37), fused:
+    u8 IQ bytes in, float phases out"""
+    h = C.c_void_p()
+    L.check(L.lib.sdr_pipe_fm_frontend(decimator.handle, blockSizeOut, C.byref(h)))
+    return NativePipe(h, decimator.ctx, np.uint8, np.float32, owner=decimator)
+
+
 def fmDemod(src: Iterable[np.ndarray], ctx=None) -> Iterator[np.ndarray]:
     """fmDemod :: Pipe (v (Complex a)) (v a) IO ()  (Demod.hs:38-46)"""
     pipe = pipeFmDemod(ctx)

@@ -392,6 +392,44 @@ def test_fm_chain_connected_pipes_vs_oracle(sdr, port):
     assert np.abs(g - w).max() <= 1e-4 * max(1.0, float(np.abs(w).max()))
 
 
+@pytest.mark.parametrize("block_out,sizes", [(8192, [16384 * 8] * 6), (1000, [16384, 2 * 3001, 2 * 300, 2 * 9000, 2 * 40000, 2 * 70000]),
+                                             (4096, [1 << 22, 1 << 22])])
+def test_fused_fm_frontend_equals_unfused_chain(sdr, port, block_out, sizes):
+    """sdr_pipe_fm_frontend == convert >-> firDecimator >-> fmDemod connected stage by stage, BIT FOR BIT (same FIR
+    summation order, same discriminator), and both match the oracle chain"""
+    ctx = sdr.default_context()
+    raw = synth.rand_bytes(sum(sizes))
+    t_dec = synth.windowed_sinc_taps(128, 1 / 16)
+    dec = sdr.cudaDecimatorC(8, t_dec, sizeMultiple=4)
+    fused = sdr.pipeFmFrontEnd(dec, block_out)
+    p0 = sdr.pipeConvertU8(ctx)
+    p1 = sdr.pipeFirDecimator(dec, block_out)
+    p2 = sdr.pipeFmDemod(ctx)
+    p0.connect(p1).connect(p2)
+    a, b, i = [], [], 0
+    used_fused = False
+    for n in sizes:
+        fused.push(raw[i:i + n])
+        p0.push(raw[i:i + n])
+        i += n
+        while fused.ready():
+            a.append(fused.pop())
+        used_fused |= sdr._lib.lib.sdr_pipe_last_kernel(fused.h).decode().startswith("fm_front_ring")
+        while p2.ready():
+            b.append(p2.pop())
+    assert len(a) == len(b) and len(a) >= 1 and all(len(v) == block_out for v in a)
+    assert used_fused
+    A, B = np.concatenate(a), np.concatenate(b)
+    assert np.array_equal(A, B), f"{int((A != B).sum())} of {len(A)} differ, first at {int(np.argmax(A != B))}"
+    # oracle chain on a prefix (CPU cost)
+    npre = min(len(raw), 16384 * 12)
+    x = port.convert_u8(raw[:npre]).view(np.complex64)
+    y = port.decimate(V_AVX, (len(x) - 128) // 8 + 1, 8, np.repeat(t_dec, 2), x, True)
+    want = port.fm_demod(y, 0j)
+    m = min(len(want), len(A))
+    assert np.abs(A[:m] - want[:m]).max() <= 2e-4   # atan2 of small products amplifies the 1e-7 FIR rounding difference
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # full-size, size-independent properties on device-resident streams
 # ---------------------------------------------------------------------------------------------------------------

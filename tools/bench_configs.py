@@ -70,25 +70,53 @@ def main():
     ctx.synth_bytes(raw, 2 * nb)
     fil = sdr_b200.cudaFilterSymR(half, ctx=ctx)
 
-    def chain():
-        p0 = sdr_b200.pipeConvertU8(ctx)
-        p1 = sdr_b200.pipeFirDecimator(d, 8192)
-        p2 = sdr_b200.pipeFmDemod(ctx)
+    # the fused front end alone: u8 IQ -> phase, device resident
+    fe = sdr_b200.pipeFmFrontEnd(d, 8192)
+    L.check(L.lib.sdr_pipe_set_batch(fe.h, 1 << 23))
+    n_out0 = C.c_longlong()
+
+    def run_fe():
+        L.check(L.lib.sdr_pipe_run(fe.h, fe.h, raw.ptr, 1 << 27, (2 * nb) >> 27, L.SDR_DEVICE, y.ptr, 2 * n, L.SDR_DEVICE, C.byref(n_out0)))
+    ms = timed(ctx, run_fe, steps=5, warmup=2)
+    report("cfg4 fused front end alone (u8 IQ -> convert -> decimate-by-8 -> fmDemod)", ms, nb, 2.5, L.lib.sdr_pipe_last_kernel(fe.h).decode())
+    fe.close()
+
+    def build_chain(fused):
+        if fused:
+            head = sdr_b200.pipeFmFrontEnd(d, 8192)
+            stages = [head]
+        else:
+            p0 = sdr_b200.pipeConvertU8(ctx)
+            p1 = sdr_b200.pipeFirDecimator(d, 8192)
+            p2 = sdr_b200.pipeFmDemod(ctx)
+            p0.connect(p1).connect(p2)
+            head, stages = p0, [p0, p1, p2]
         p3 = sdr_b200.pipeFirResampler(r, 8192)
         p4 = sdr_b200.pipeFirFilter(fil, 8192)
         p5 = sdr_b200.pipeScale(0.2, ctx)
-        p0.connect(p1).connect(p2).connect(p3).connect(p4).connect(p5)
-        for p in (p1, p3, p4):
-            L.check(L.lib.sdr_pipe_set_batch(p.h, 1 << 22))
+        stages[-1].connect(p3).connect(p4).connect(p5)
+        stages += [p3, p4, p5]
+        for p in stages:
+            if p is not p5 and p.in_dtype != np.uint8 or (fused and p is head):
+                try:
+                    L.check(L.lib.sdr_pipe_set_batch(p.h, 1 << 21))
+                except sdr_b200.SdrError:
+                    pass
+        return head, p5, stages
+
+    for fused in (False, True):
+        head, tail, stages = build_chain(fused)
         n_out = C.c_longlong()
-        chunk = 1 << 24   # bytes per push (device memory): 8M IQ pairs
-        L.check(L.lib.sdr_pipe_run(p0.h, p5.h, raw.ptr, chunk, (2 * nb) // chunk, L.SDR_DEVICE, y.ptr, 2 * n, L.SDR_DEVICE,
-                                   C.byref(n_out)))
-        for p in (p0, p1, p2, p3, p4, p5):
+        chunk = 1 << 25   # bytes per push (device memory): 16M IQ pairs
+
+        def run():
+            L.check(L.lib.sdr_pipe_run(head.h, tail.h, raw.ptr, chunk, (2 * nb) // chunk, L.SDR_DEVICE, y.ptr, 2 * n, L.SDR_DEVICE,
+                                       C.byref(n_out)))
+        ms = timed(ctx, run, steps=5, warmup=2)
+        kern = L.lib.sdr_pipe_last_kernel(head.h).decode() if fused else ""
+        report("cfg4 FM chain u8 IQ -> audio, device pipes, " + ("fused front end" if fused else "stage by stage"), ms, nb, 2.15, kern)
+        for p in stages:
             p.close()
-        return n_out.value
-    ms = timed(ctx, chain, steps=3, warmup=1)
-    report("cfg4 FM chain (u8 IQ -> audio), connected pipes, un-fused", ms, nb, 2.15)
 
 
 if __name__ == "__main__":
