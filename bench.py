@@ -298,6 +298,16 @@ def run_e2e(args, ctx, dec, plan, rank, world, dist, sdr_b200, L):
         pipe.close()
         return n_out.value
 
+    # the PCIe ceiling of this box, measured the plain way: one pinned host-to-device copy of the whole input
+    dtmp = ctx.alloc(hin.array.nbytes)
+    ev0, ev1 = sdr_b200.Event(ctx), sdr_b200.Event(ctx)
+    L.check(L.lib.sdr_memcpy_h2d(ctx.h, dtmp.ptr, hin.p, hin.array.nbytes))
+    ev0.record()
+    L.check(L.lib.sdr_memcpy_h2d(ctx.h, dtmp.ptr, hin.p, hin.array.nbytes))
+    ev1.record()
+    h2d_gbs = hin.array.nbytes / (ev0.elapsed_ms(ev1) * 1e-3) / 1e9
+    dtmp.free()
+
     steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(2):
         one_pass()
@@ -340,7 +350,10 @@ def run_e2e(args, ctx, dec, plan, rank, world, dist, sdr_b200, L):
            "d2h_bytes_per_step": int(8 * got), "steps": steps,
            "api": "sdr_pipe_run(firDecimator, 8192-sample pinned host vectors in, 8192-sample host vectors out), "
                   f"sdr_pipe_set_batch = {args.e2e_batch_vectors} output vectors per launch",
-           "spot_parity_vs_reference_avx": ok}
+           "spot_parity_vs_reference_avx": ok,
+           "pcie_h2d_GBps_plain_memcpy": h2d_gbs,
+           "h2d_GBps_achieved": 8.0 * (n_vecs * BUF) / (ms / steps * 1e-3) / 1e9,
+           "bound": "PCIe host-to-device: 8 B per input sample must cross the link"}
     hin.free()
     hout.free()
     return res

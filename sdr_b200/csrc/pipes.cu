@@ -64,14 +64,15 @@ struct TraceRec { const char *label; long long n; cudaEvent_t e0, e1; double hos
 static std::deque<TraceRec> &trace_log() { static std::deque<TraceRec> q; return q; }
 struct TraceScope {
     const char *label; Ctx *c; long long n; std::chrono::steady_clock::time_point t0; cudaEvent_t e0 = nullptr;
+    static bool active() { return trace_mode() == 1 || trace_mode() == 2; }   // 3 = run-level timing only
     TraceScope(const char *l, Ctx *ctx, long long count) : label(l), c(ctx), n(count) {
-        if (!trace_mode()) return;
+        if (!active()) return;
         if (trace_mode() == 1) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->side); }
         else { cudaEventCreate(&e0); cudaEventRecord(e0, c->stream); }
         t0 = std::chrono::steady_clock::now();
     }
     ~TraceScope() {
-        if (!trace_mode()) return;
+        if (!active()) return;
         if (trace_mode() == 1) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->side); }
         double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
         if (trace_mode() == 1) { fprintf(stderr, "[sdr_b200 trace] %-18s n=%-10lld %9.1f us\n", label, n, us); return; }
@@ -293,6 +294,8 @@ static int fetch(sdr_pipe *p, void *d_dst, const void *src, size_t bytes, int me
     if (mem == SDR_HOST_PINNED) {
         if (p->pend_bytes && p->pend_src + p->pend_bytes == (const char *)src && p->pend_dst + p->pend_bytes == (char *)d_dst) {
             p->pend_bytes += bytes;   // extends the deferred copy
+            // keep the DMA engine busy while the host is still collecting the rest of the batch
+            if (p->pend_bytes >= ((size_t)8 << 20)) SDR_TRY(flush_pending(p));
             return SDR_OK;
         }
         SDR_TRY(flush_pending(p));
@@ -311,8 +314,10 @@ static int fetch(sdr_pipe *p, void *d_dst, const void *src, size_t bytes, int me
     return SDR_OK;
 }
 
+static thread_local bool g_bound = false;   // sdr_pipe_run binds the device once for its whole loop
+
 static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, long long n_vecs) {
-    SDR_TRY(p->ctx->bind());
+    if (!g_bound) SDR_TRY(p->ctx->bind());
     TraceScope tr_push("push(total)", p->ctx, n);
     if (is_fir_kind(p->kind)) {
         // the reference asserts every awaited vector holds at least numCoeffs samples (Filter.hs:544,586,691)
@@ -546,6 +551,7 @@ int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_
     long long written = 0;
     SDR_TRY(p->ctx->bind());
     auto t_start = std::chrono::steady_clock::now();
+    struct BoundGuard { BoundGuard() { g_bound = true; } ~BoundGuard() { g_bound = false; } } bound_guard;
     for (long long v = 0; v < n_vecs; v++) {
         SDR_TRY(pipe_push_any(p, (const char *)in + (size_t)(v * vec_len) * p->in_eb, vec_len, in_mem));
         SDR_TRY(drain(sink, out, out_capacity, out_mem, &written));
