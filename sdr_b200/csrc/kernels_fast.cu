@@ -46,6 +46,7 @@ k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const floa
     typedef RingCfg<T, D, R> C;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
 
     // contiguous, balanced range of sub-tiles for this CTA
     long long q = n_sub / gridDim.x, rem = n_sub % gridDim.x;
@@ -113,9 +114,16 @@ k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const floa
                 }
             }
         }
-        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + (s0 + u) * (long long)C::SUB_OUT + lane * R);
+        float2 *os = out + (s0 + u) * (long long)C::SUB_OUT + lane * R;
+        if (vec_store) {
+            ulonglong2 *o = reinterpret_cast<ulonglong2 *>(os);
 #pragma unroll
-        for (int r = 0; r < R; r += 2) o[r / 2] = make_ulonglong2(acc[r], acc[r + 1]);
+            for (int r = 0; r < R; r += 2) o[r / 2] = make_ulonglong2(acc[r], acc[r + 1]);
+        } else {   // output only 8-byte aligned (a pipe's FIFO cursor after an odd number of outputs)
+            u64 *o = reinterpret_cast<u64 *>(os);
+#pragma unroll
+            for (int r = 0; r < R; r++) o[r] = acc[r];
+        }
 
         __syncwarp();
         if (lane == 0) {
@@ -160,7 +168,7 @@ int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_
                       long long num, long long *done, const char **name) {
     *done = 0;
     *name = "fir_direct";
-    if ((((uintptr_t)d_in | (uintptr_t)d_out) & 15) != 0) return SDR_OK;   // TMA bulk copies need 16-byte alignment
+    if ((((uintptr_t)d_in) & 15) != 0) return SDR_OK;   // TMA bulk copies need a 16-byte aligned source; any output alignment
     if (T == 128 && D == 8) {
         *name = "dec_c_ring<128,8,8>";
         return launch_ring<128, 8, 8>(c, d_taps, d_in, n_in, d_out, num, done);

@@ -66,13 +66,13 @@ struct TraceScope {
     const char *label; Ctx *c; long long n; std::chrono::steady_clock::time_point t0; cudaEvent_t e0 = nullptr;
     static bool active() { return trace_mode() == 1 || trace_mode() == 2; }   // 3 = run-level timing only
     TraceScope(const char *l, Ctx *ctx, long long count) : label(l), c(ctx), n(count) {
-        if (!active()) return;
+        if (!active() || !label) return;
         if (trace_mode() == 1) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->side); }
         else { cudaEventCreate(&e0); cudaEventRecord(e0, c->stream); }
         t0 = std::chrono::steady_clock::now();
     }
     ~TraceScope() {
-        if (!active()) return;
+        if (!active() || !label) return;
         if (trace_mode() == 1) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->side); }
         double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
         if (trace_mode() == 1) { fprintf(stderr, "[sdr_b200 trace] %-18s n=%-10lld %9.1f us\n", label, n, us); return; }
@@ -125,6 +125,10 @@ struct sdr_pipe {
     const char *assert_name = "";
     // SDR_HOST_PINNED pushes: host-to-device copies of vectors that are contiguous on both sides are merged and
     // issued only when a launch needs the data (one DMA per output vector instead of one per input vector)
+    // full-duplex drain (sdr_pipe_run, pinned output): device-to-host copies ride the side stream so they overlap the
+    // next batch's host-to-device copies; the FIFO may not be rewritten before the copy has finished
+    cudaEvent_t ev_out_ready = nullptr, ev_out_done = nullptr;
+    bool d2h_outstanding = false;
     long long batch_min = 0;          // launch only once this many new outputs are computable (0: one output vector)
     const char *pend_src = nullptr;
     char *pend_dst = nullptr;
@@ -135,8 +139,14 @@ namespace sdr {
 
 static bool is_fir_kind(int k) { return k == P_FILTER || k == P_DECIM || k == P_RESAMP || k == P_FMFRONT; }
 
+static int fifo_writable(sdr_pipe *p) {
+    if (p->d2h_outstanding) { SDR_CUDA(cudaStreamWaitEvent(p->ctx->stream, p->ev_out_done, 0)); p->d2h_outstanding = false; }
+    return SDR_OK;
+}
+
 static int flush_pending(sdr_pipe *p) {
     if (p->pend_bytes) {
+        TraceScope tr("h2d", p->ctx, (long long)p->pend_bytes);
         SDR_CUDA(cudaMemcpyAsync(p->pend_dst, p->pend_src, p->pend_bytes, cudaMemcpyHostToDevice, p->ctx->stream));
         p->pend_bytes = 0; p->pend_src = nullptr; p->pend_dst = nullptr;
     }
@@ -216,6 +226,7 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     if (!(count > 0 && fifo_have + count >= p->block_out && fifo_have + count >= batch)) return SDR_OK;
     SDR_TRY(flush_pending(p));
     TraceScope tr("fm_front", p->ctx, count);
+    SDR_TRY(fifo_writable(p));
     SDR_TRY(p->fifo.reserve((size_t)count * 4));
     float *out = (float *)(p->fifo.p + p->fifo.wr);
     p->bnd.rd = p->bnd.wr = 0;
@@ -235,6 +246,7 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     p->last_sel ^= 1;
     p->fifo.wr += (size_t)count * 4;
     p->in.rd += (size_t)(count * f.D) * 2;
+    if (p->in.size() <= (1u << 16) && p->in.rd > p->in.cap / 4) SDR_TRY(p->in.realign(0));
     return SDR_OK;
 }
 
@@ -253,6 +265,7 @@ static int process_fir(sdr_pipe *p, bool force = false) {
             SDR_TRY(flush_pending(p));
             TraceScope tr("resampler", p->ctx, count);
             long long i_k = (p->k_next * r.M + r.L - 1) / r.L;   // ceil(k M / L): first sample of output k
+            SDR_TRY(fifo_writable(p));
             SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
             Seg2 seg = {p->in.p + p->in.rd, have, nullptr, 0};
             SDR_TRY(r.run(seg, i_k - p->pos, (int)(p->k_next % r.ng), p->fifo.p + p->fifo.wr, count, false));
@@ -278,12 +291,15 @@ static int process_fir(sdr_pipe *p, bool force = false) {
     if (count > 0 && fifo_have + count >= p->block_out && (fifo_have + count >= batch)) {
         SDR_TRY(flush_pending(p));
         TraceScope tr(p->kind == P_FILTER ? "filter" : "decimator", p->ctx, count);
+        SDR_TRY(fifo_writable(p));
         SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
         Seg2 seg = {p->in.p + p->in.rd, have, nullptr, 0};
         SDR_TRY(f.run(seg, 0, p->fifo.p + p->fifo.wr, count, false));
         p->fifo.wr += (size_t)count * p->out_eb;
         p->in.rd += (size_t)(count * f.D) * p->in_eb;
-        if ((p->in.rd & 15) && p->in.size() <= (1u << 16)) SDR_TRY(p->in.realign(0));   // keep the tuned kernels' 16-byte alignment
+        // park the short tail at the front right after a launch: keeps the tuned kernels' 16-byte alignment and means
+        // the buffer never has to slide while it holds a half-collected batch
+        if (p->in.size() <= (1u << 16) && ((p->in.rd & 15) || p->in.rd > p->in.cap / 4)) SDR_TRY(p->in.realign(0));
     }
     return SDR_OK;
 }
@@ -318,7 +334,7 @@ static thread_local bool g_bound = false;   // sdr_pipe_run binds the device onc
 
 static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, long long n_vecs) {
     if (!g_bound) SDR_TRY(p->ctx->bind());
-    TraceScope tr_push("push(total)", p->ctx, n);
+    TraceScope tr_push(trace_mode() == 1 ? "push(total)" : nullptr, p->ctx, n);
     if (is_fir_kind(p->kind)) {
         // the reference asserts every awaited vector holds at least numCoeffs samples (Filter.hs:544,586,691)
         long long need = (p->kind == P_RESAMP) ? (p->res->T + p->res->L - 1) / p->res->L : p->fir->T;
@@ -349,6 +365,7 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, lon
         if (n & 1) return set_error(SDR_EINVAL, "convert pipe: odd byte count %lld (interleaved I/Q pairs expected)", n);
         n_out = n / 2;   // complex samples out
     }
+    SDR_TRY(fifo_writable(p));
     SDR_TRY(p->fifo.reserve((size_t)n_out * p->out_eb));
     void *d_dst = p->fifo.p + p->fifo.wr;
     if (p->kind == P_CONVERT) SDR_TRY(launch_convert_u8(p->ctx, (const uint8_t *)d_src, (float *)d_dst, n));
@@ -436,8 +453,11 @@ int sdr_pipe_destroy(sdr_pipe_t *p) {
     if (!p) return SDR_OK;
     p->ctx->bind();
     cudaStreamSynchronize(p->ctx->stream);
+    cudaStreamSynchronize(p->ctx->side);
     p->in.release(); p->fifo.release(); p->bnd.release(); p->scratch_x.release(); p->scratch_y.release();
     if (p->d_last) cudaFree(p->d_last);
+    if (p->ev_out_ready) cudaEventDestroy(p->ev_out_ready);
+    if (p->ev_out_done) cudaEventDestroy(p->ev_out_done);
     delete p;
     return SDR_OK;
 }
@@ -480,6 +500,7 @@ int sdr_pipe_pop(sdr_pipe_t *p, void *out, long long *n_out, int mem) {
         p->vec_lens.pop_front();
     }
     SDR_TRY(p->ctx->bind());
+    SDR_TRY(fifo_writable(p));
     size_t bytes = (size_t)n * p->out_eb;
     if (bytes)
         SDR_CUDA(cudaMemcpyAsync(out, p->fifo.p + p->fifo.rd, bytes,
@@ -495,6 +516,7 @@ int sdr_pipe_sync(sdr_pipe_t *p) {
     SDR_TRY(p->ctx->bind());
     SDR_TRY(flush_pending(p));
     SDR_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    SDR_CUDA(cudaStreamSynchronize(p->ctx->side));
     trace_dump();
     return SDR_OK;
 }
@@ -521,9 +543,24 @@ static int drain(sdr_pipe *sink, void *out, long long out_capacity, int out_mem,
         if (nb == 0) return SDR_OK;
         long long n = nb * sink->block_out;
         if (*written + n > out_capacity) return set_error(SDR_EINVAL, "sdr_pipe_run: output capacity %lld too small", out_capacity);
-        SDR_CUDA(cudaMemcpyAsync((char *)out + (size_t)*written * sink->out_eb, sink->fifo.p + sink->fifo.rd, (size_t)n * sink->out_eb,
-                                 out_mem == SDR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sink->ctx->stream));
-        if (out_mem == SDR_HOST) SDR_CUDA(cudaStreamSynchronize(sink->ctx->stream));
+        TraceScope tr("drain", sink->ctx, n);
+        if (out_mem == SDR_HOST_PINNED) {
+            if (!sink->ev_out_ready) {
+                SDR_CUDA(cudaEventCreateWithFlags(&sink->ev_out_ready, cudaEventDisableTiming));
+                SDR_CUDA(cudaEventCreateWithFlags(&sink->ev_out_done, cudaEventDisableTiming));
+            }
+            SDR_TRY(fifo_writable(sink));   // at most one copy in flight per stage
+            SDR_CUDA(cudaEventRecord(sink->ev_out_ready, sink->ctx->stream));
+            SDR_CUDA(cudaStreamWaitEvent(sink->ctx->side, sink->ev_out_ready, 0));
+            SDR_CUDA(cudaMemcpyAsync((char *)out + (size_t)*written * sink->out_eb, sink->fifo.p + sink->fifo.rd, (size_t)n * sink->out_eb,
+                                     cudaMemcpyDeviceToHost, sink->ctx->side));
+            SDR_CUDA(cudaEventRecord(sink->ev_out_done, sink->ctx->side));
+            sink->d2h_outstanding = true;
+        } else {
+            SDR_CUDA(cudaMemcpyAsync((char *)out + (size_t)*written * sink->out_eb, sink->fifo.p + sink->fifo.rd, (size_t)n * sink->out_eb,
+                                     out_mem == SDR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sink->ctx->stream));
+            if (out_mem == SDR_HOST) SDR_CUDA(cudaStreamSynchronize(sink->ctx->stream));
+        }
         sink->fifo.consume((size_t)n * sink->out_eb);
         *written += n;
         return SDR_OK;
