@@ -154,6 +154,11 @@ int dcBlockerCuda(int num, float lastSample, float lastOutput, float *finalSampl
  * the previous buffer's final sample, (0,0) at stream start (Demod.hs:41) */
 int fmDemodCuda(int num, float lastRe, float lastIm, const float *in, float *out);
 
+/* the element-wise kernels on DEVICE-resident buffers (enqueue-only on the ctx stream) */
+int sdr_dev_convert_u8(sdr_ctx_t *ctx, const uint8_t *d_in, float *d_out, long long n_bytes);   /* convert.c:15 */
+int sdr_dev_scale(sdr_ctx_t *ctx, float factor, const float *d_in, float *d_out, long long n);  /* scale.c:15   */
+int sdr_dev_fm_demod(sdr_ctx_t *ctx, float last_re, float last_im, const float *d_in, float *d_out, long long n); /* Demod.hs:32 */
+
 /* ---------------------------------------------------------------------------------------------------------- */
 /* Verification entry points: SDR_ARITH_EXACT arithmetic of ONE named reference variant, HOST pointers.           */
 /* `coeffs` / `numCoeffs` exactly as that reference function receives them (plain, duplicated or half).           */
@@ -258,6 +263,7 @@ int sdr_pipe_fm_frontend(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **p)
 const char *sdr_pipe_last_kernel(const sdr_pipe_t *p);
 int sdr_pipe_convert_u8(sdr_ctx_t *ctx, sdr_pipe_t **p); /* P.map interleavedIQUnsignedByteToFloat (Util.hs:104) */
 int sdr_pipe_scale(sdr_ctx_t *ctx, float factor, sdr_pipe_t **p);                   /* P.map (VG.map (* k)) fm.hs:40 */
+int sdr_pipe_dc_blocker(sdr_ctx_t *ctx, sdr_pipe_t **p);                            /* dcBlockingFilter Filter.hs:730 */
 int sdr_pipe_destroy(sdr_pipe_t *p);
 /* feed one upstream vector of n INPUT elements (for convert_u8: n bytes).  Fails with SDR_EPRECOND
  * ("filter 1" / "decimate 1" / "resample 1") when the very first / a post-drain vector is shorter than numCoeffs. */

@@ -8,7 +8,7 @@ from .device import Context, DeviceBuffer, Event, PinnedArray, device_count, has
 from .filter import (Decimator, Filter, NativePipe, Resampler, cudaDecimatorC, cudaDecimatorR, cudaDecimatorSymR,  # noqa: F401
                      cudaFilterC, cudaFilterR, cudaFilterSymR, cudaResamplerC, cudaResamplerR, default_context,
                      firDecimator, firFilter, firResampler, pipeFirDecimator, pipeFirFilter, pipeFirResampler)
-from .util import (complexFloatToInterleavedIQSigned2048, dcBlocker, fmDemod, fmDemodVec,  # noqa: F401
+from .util import (complexFloatToInterleavedIQSigned2048, dcBlocker, dcBlockingFilter, fmDemod, pipeDcBlocker, fmDemodVec,  # noqa: F401
                    interleavedIQSigned2048ToFloat, interleavedIQUnsignedByteToFloat, pipeConvertU8, pipeFmDemod, pipeFmFrontEnd,
                    pipeScale, scaleFast)
 from . import multigpu  # noqa: F401

@@ -139,6 +139,7 @@ lib.sdr_pipe_last_kernel.restype = C.c_char_p
 lib.sdr_pipe_last_kernel.argtypes = [C.c_void_p]
 _sig("sdr_pipe_convert_u8", _P, c_void_pp)
 _sig("sdr_pipe_scale", _P, _F, c_void_pp)
+_sig("sdr_pipe_dc_blocker", _P, c_void_pp)
 _sig("sdr_pipe_destroy", _P)
 _sig("sdr_pipe_push", _P, _P, _LL, _I)
 _sig("sdr_pipe_ready", _P, C.POINTER(_I))

@@ -73,6 +73,7 @@ int launch_fm_demod(Ctx *c, float last_re, float last_im, const float *d_in, flo
 int launch_fm_demod_carry(Ctx *c, const float *d_last, const float *d_in, float *d_out, long long n);
 int launch_dc_blocker(Ctx *c, float last_sample, float last_output, const float *d_in, float *d_out, long long n,
                       float *d_final2);
+int launch_dc_blocker_carry(Ctx *c, float *d_state, const float *d_in, float *d_out, long long n);
 int launch_synth_noise(Ctx *c, float *d_out, long long n, long long first, uint32_t seed);
 int launch_synth_bytes(Ctx *c, uint8_t *d_out, long long n, long long first, uint32_t seed);
 int launch_checksum32(Ctx *c, const uint32_t *d_buf, long long n, long long first, unsigned long long *d_sum);

@@ -297,14 +297,21 @@ int launch_resample_exact(Ctx *c, bool cplx, int taps_per_group, int row_stride,
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float cvt_u8(unsigned b) { return __fmul_rn(__fsub_rn((float)b, 128.0f), 1.0f / 128.0f); }
 
-__global__ void __launch_bounds__(256) k_convert_u8_vec(const uint4 *__restrict__ in, float4 *__restrict__ out, long long n16) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
-        uint4 v = __ldg(in + i);
-        unsigned w[4] = {v.x, v.y, v.z, v.w};
+// one 32-bit word (4 bytes) in, one float4 out per thread and trip: both sides fully coalesced; 4 trips in flight
+__global__ void __launch_bounds__(256) k_convert_u8_vec(const uint32_t *__restrict__ in, float4 *__restrict__ out, long long n4) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) w[q] = __ldg(in + i + q * stride);
 #pragma unroll
         for (int q = 0; q < 4; q++)
-            out[4 * i + q] = make_float4(cvt_u8(w[q] & 0xff), cvt_u8((w[q] >> 8) & 0xff), cvt_u8((w[q] >> 16) & 0xff),
-                                         cvt_u8(w[q] >> 24));
+            out[i + q * stride] = make_float4(cvt_u8(w[q] & 0xff), cvt_u8((w[q] >> 8) & 0xff), cvt_u8((w[q] >> 16) & 0xff), cvt_u8(w[q] >> 24));
+    }
+    for (; i < n4; i += stride) {
+        uint32_t w = __ldg(in + i);
+        out[i] = make_float4(cvt_u8(w & 0xff), cvt_u8((w >> 8) & 0xff), cvt_u8((w >> 16) & 0xff), cvt_u8(w >> 24));
     }
 }
 __global__ void __launch_bounds__(256) k_convert_u8(const uint8_t *__restrict__ in, float *__restrict__ out, long long n) {
@@ -316,11 +323,11 @@ int launch_convert_u8(Ctx *c, const uint8_t *d_in, float *d_out, long long n) {
     if (n <= 0) return SDR_OK;
     SDR_TRY(c->bind());
     long long nv = 0;
-    if ((((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0) nv = n / 16;
-    if (nv) { k_convert_u8_vec<<<grid_for(nv, 256, c->sm_count), 256, 0, c->s()>>>((const uint4 *)d_in, (float4 *)d_out, nv);
+    if ((((uintptr_t)d_in) & 3) == 0 && (((uintptr_t)d_out) & 15) == 0) nv = n / 4;
+    if (nv) { k_convert_u8_vec<<<grid_for(nv, 256, c->sm_count, 8), 256, 0, c->s()>>>((const uint32_t *)d_in, (float4 *)d_out, nv);
               SDR_LAUNCH_CHECK(c); }
-    long long rest = n - nv * 16;
-    if (rest) { k_convert_u8<<<grid_for(rest, 256, c->sm_count), 256, 0, c->s()>>>(d_in + nv * 16, d_out + nv * 16, rest);
+    long long rest = n - nv * 4;
+    if (rest) { k_convert_u8<<<grid_for(rest, 256, c->sm_count), 256, 0, c->s()>>>(d_in + nv * 4, d_out + nv * 4, rest);
                 SDR_LAUNCH_CHECK(c); }
     return SDR_OK;
 }
@@ -380,37 +387,57 @@ int launch_scale(Ctx *c, float k, const float *d_in, float *d_out, long long n) 
     return SDR_OK;
 }
 
+// 4 consecutive samples per thread: two 16-byte loads (+ one L1-resident re-read for the predecessor of the first
+// sample), four independent branch-free discriminators, one 16-byte store
+__global__ void __launch_bounds__(256) k_fm_demod4(float last_re, float last_im, const float2 *__restrict__ last_ptr,
+                                                   const float4 *__restrict__ in, float4 *__restrict__ out, long long n4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
+        const float2 s0 = make_float2(a.x, a.y), s1 = make_float2(a.z, a.w), s2 = make_float2(b.x, b.y), s3 = make_float2(b.z, b.w);
+        float2 l;
+        if (i == 0) l = last_ptr ? *last_ptr : make_float2(last_re, last_im);
+        else { const float4 p = __ldg(in + 2 * i - 1); l = make_float2(p.z, p.w); }
+        out[i] = make_float4(fm_phase(s0, l), fm_phase(s1, s0), fm_phase(s2, s1), fm_phase(s3, s2));
+    }
+}
 __global__ void __launch_bounds__(256) k_fm_demod(float last_re, float last_im, const float2 *__restrict__ last_ptr,
-                                                  const float2 *__restrict__ in, float *__restrict__ out, long long n) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+                                                  const float2 *__restrict__ in, float *__restrict__ out, long long first, long long n) {
+    for (long long i = first + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float2 s = __ldg(in + i);
         float2 l = (i == 0) ? (last_ptr ? *last_ptr : make_float2(last_re, last_im)) : __ldg(in + i - 1);
         out[i] = fm_phase(s, l);
     }
 }
-int launch_fm_demod(Ctx *c, float last_re, float last_im, const float *d_in, float *d_out, long long n) {
+static int launch_fm_demod_any(Ctx *c, float last_re, float last_im, const float *d_last, const float *d_in, float *d_out, long long n) {
     if (n <= 0) return SDR_OK;
     SDR_TRY(c->bind());
-    k_fm_demod<<<grid_for(n, 256, c->sm_count), 256, 0, c->s()>>>(last_re, last_im, nullptr, (const float2 *)d_in, d_out, n);
-    SDR_LAUNCH_CHECK(c);
+    long long n4 = 0;
+    if ((((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0) n4 = n / 4;
+    if (n4) { k_fm_demod4<<<grid_for(n4, 256, c->sm_count, 8), 256, 0, c->s()>>>(last_re, last_im, (const float2 *)d_last, (const float4 *)d_in,
+                                                                               (float4 *)d_out, n4);
+              SDR_LAUNCH_CHECK(c); }
+    if (4 * n4 < n) { k_fm_demod<<<grid_for(n - 4 * n4, 256, c->sm_count), 256, 0, c->s()>>>(last_re, last_im, (const float2 *)d_last,
+                                                                                            (const float2 *)d_in, d_out, 4 * n4, n);
+                      SDR_LAUNCH_CHECK(c); }
     return SDR_OK;
+}
+int launch_fm_demod(Ctx *c, float last_re, float last_im, const float *d_in, float *d_out, long long n) {
+    return launch_fm_demod_any(c, last_re, last_im, nullptr, d_in, d_out, n);
 }
 // streaming form: the previous buffer's final sample is read from device memory (fmDemod's carried state, Demod.hs:46)
 int launch_fm_demod_carry(Ctx *c, const float *d_last, const float *d_in, float *d_out, long long n) {
-    if (n <= 0) return SDR_OK;
-    SDR_TRY(c->bind());
-    k_fm_demod<<<grid_for(n, 256, c->sm_count), 256, 0, c->s()>>>(0.0f, 0.0f, (const float2 *)d_last, (const float2 *)d_in, d_out, n);
-    SDR_LAUNCH_CHECK(c);
-    return SDR_OK;
+    return launch_fm_demod_any(c, 0.0f, 0.0f, d_last, d_in, d_out, n);
 }
 
 // dcBlocker (filter.c:152-161): y[n] = (x[n] - x[n-1]) + 0.997 * y[n-1]; the difference is a float subtraction, the
 // product and sum are evaluated in double (0.997 is a double literal) and rounded to float on the store.  Each y[n]
 // depends on the ROUNDED y[n-1], so the recurrence is evaluated serially by one lane (bit-exact); the warp only
 // streams the data through shared memory in coalesced 1024-sample chunks.
-__global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last_output, const float *__restrict__ in,
-                                                   float *__restrict__ out, long long n, float *__restrict__ final2) {
+__global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last_output, const float *__restrict__ state_in,
+                                                   const float *__restrict__ in, float *__restrict__ out, long long n,
+                                                   float *__restrict__ final2) {
     __shared__ float buf[1024];
+    if (state_in) { last_sample = state_in[0]; last_output = state_in[1]; }   // streaming form: state carried on the device
     for (long long base = 0; base < n; base += 1024) {
         int m = (int)((n - base) < 1024 ? (n - base) : 1024);
         for (int i = threadIdx.x; i < m; i += 32) buf[i] = in[base + i];
@@ -433,7 +460,15 @@ __global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last
 int launch_dc_blocker(Ctx *c, float last_sample, float last_output, const float *d_in, float *d_out, long long n,
                       float *d_final2) {
     SDR_TRY(c->bind());
-    k_dc_blocker<<<1, 32, 0, c->s()>>>(last_sample, last_output, d_in, d_out, n, d_final2);
+    k_dc_blocker<<<1, 32, 0, c->s()>>>(last_sample, last_output, nullptr, d_in, d_out, n, d_final2);
+    SDR_LAUNCH_CHECK(c);
+    return SDR_OK;
+}
+// d_state: (lastSample, lastOutput) on the device, read before and updated after the block (dcBlockingFilter's pMapAccum)
+int launch_dc_blocker_carry(Ctx *c, float *d_state, const float *d_in, float *d_out, long long n) {
+    if (n <= 0) return SDR_OK;
+    SDR_TRY(c->bind());
+    k_dc_blocker<<<1, 32, 0, c->s()>>>(0.0f, 0.0f, d_state, d_in, d_out, n, d_state);
     SDR_LAUNCH_CHECK(c);
     return SDR_OK;
 }

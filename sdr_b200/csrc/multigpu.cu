@@ -222,6 +222,23 @@ int sdr_decimate_sharded(sdr_decimator_t *d, sdr_comm_t *c, const sdr_shard_t *p
     return SDR_OK;
 }
 
+// ---- element-wise kernels on device-resident buffers (enqueue-only; the one-shot layer-1 symbols stage host memory) ----
+int sdr_dev_convert_u8(sdr_ctx_t *ctx, const uint8_t *d_in, float *d_out, long long n_bytes) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || n_bytes < 0 || (n_bytes && (!d_in || !d_out))) return set_error(SDR_EINVAL, "sdr_dev_convert_u8: bad argument");
+    return launch_convert_u8(c, d_in, d_out, n_bytes);
+}
+int sdr_dev_scale(sdr_ctx_t *ctx, float factor, const float *d_in, float *d_out, long long n) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || n < 0 || (n && (!d_in || !d_out))) return set_error(SDR_EINVAL, "sdr_dev_scale: bad argument");
+    return launch_scale(c, factor, d_in, d_out, n);
+}
+int sdr_dev_fm_demod(sdr_ctx_t *ctx, float last_re, float last_im, const float *d_in, float *d_out, long long n) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || n < 0 || (n && (!d_in || !d_out))) return set_error(SDR_EINVAL, "sdr_dev_fm_demod: bad argument");
+    return launch_fm_demod(c, last_re, last_im, d_in, d_out, n);
+}
+
 // ---- synthetic streams + measurement helpers -----------------------------------------------------------------------
 int sdr_synth_noise(sdr_ctx_t *ctx, float *d_out, long long n_floats, long long first_float, uint32_t seed) {
     Ctx *c = reinterpret_cast<Ctx *>(ctx);

@@ -95,7 +95,7 @@ static void trace_dump() {
     trace_log().clear();
 }
 
-enum { P_FILTER, P_DECIM, P_RESAMP, P_FMDEMOD, P_CONVERT, P_SCALE, P_FMFRONT };
+enum { P_FILTER, P_DECIM, P_RESAMP, P_FMDEMOD, P_CONVERT, P_SCALE, P_FMFRONT, P_DCBLOCK };
 
 }  // namespace sdr
 
@@ -370,6 +370,7 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, lon
     void *d_dst = p->fifo.p + p->fifo.wr;
     if (p->kind == P_CONVERT) SDR_TRY(launch_convert_u8(p->ctx, (const uint8_t *)d_src, (float *)d_dst, n));
     else if (p->kind == P_SCALE) SDR_TRY(launch_scale(p->ctx, p->scale_k, (const float *)d_src, (float *)d_dst, n));
+    else if (p->kind == P_DCBLOCK) SDR_TRY(launch_dc_blocker_carry(p->ctx, p->d_last, (const float *)d_src, (float *)d_dst, n));
     else {
         SDR_TRY(launch_fm_demod_carry(p->ctx, p->d_last, (const float *)d_src, (float *)d_dst, n));
         if (n) SDR_CUDA(cudaMemcpyAsync(p->d_last, (const char *)d_src + (size_t)(n - 1) * 8, 8, cudaMemcpyDeviceToDevice, p->ctx->stream));
@@ -447,6 +448,14 @@ int sdr_pipe_scale(sdr_ctx_t *ctx, float factor, sdr_pipe_t **out) {
     sdr_pipe *p;
     SDR_TRY(new_pipe(reinterpret_cast<Ctx *>(ctx), P_SCALE, out, &p));
     p->in_eb = p->out_eb = 4; p->scale_k = factor;
+    return SDR_OK;
+}
+int sdr_pipe_dc_blocker(sdr_ctx_t *ctx, sdr_pipe_t **out) {
+    sdr_pipe *p;
+    SDR_TRY(new_pipe(reinterpret_cast<Ctx *>(ctx), P_DCBLOCK, out, &p));
+    p->in_eb = p->out_eb = 4;
+    SDR_CUDA(cudaMalloc(&p->d_last, 8));   // (lastSample, lastOutput), both 0 at stream start (Filter.hs:731)
+    SDR_CUDA(cudaMemsetAsync(p->d_last, 0, 8, p->ctx->stream));
     return SDR_OK;
 }
 int sdr_pipe_destroy(sdr_pipe_t *p) {

@@ -82,6 +82,24 @@ def pipeScale(factor, ctx=None) -> NativePipe:
     return NativePipe(h, ctx, np.float32, np.float32)
 
 
+def pipeDcBlocker(ctx=None) -> NativePipe:
+    ctx = ctx or default_context()
+    h = C.c_void_p()
+    L.check(L.lib.sdr_pipe_dc_blocker(ctx.h, C.byref(h)))
+    return NativePipe(h, ctx, np.float32, np.float32)
+
+
+def dcBlockingFilter(src: Iterable[np.ndarray], ctx=None) -> Iterator[np.ndarray]:
+    """dcBlockingFilter :: Pipe (VS.Vector Float) (VS.Vector Float) IO ()  (Filter.hs:730-739)"""
+    pipe = pipeDcBlocker(ctx)
+    try:
+        for vec in src:
+            pipe.push(vec)
+            yield pipe.pop()
+    finally:
+        pipe.close()
+
+
 def pipeFmFrontEnd(decimator, blockSizeOut) -> NativePipe:
     """P.map interleavedIQUnsignedByteToFloat >-> firDecimator decimator blockSizeOut >-> fmDemod  (fm.hs:34-37), fused:
     u8 IQ bytes in, float phases out"""

@@ -250,6 +250,15 @@ def test_fm_demod_vs_oracle(sdr, port):
     assert np.array_equal(np.concatenate(outs), got)
 
 
+def test_dc_blocking_filter_pipe_bitexact(sdr, ref):
+    """dcBlockingFilter (Filter.hs:730-739): state carried across vectors; bit-exact vs the reference C run on the flat stream"""
+    x = rnd(3 * 4096 + 77, False, 12)
+    chunks = [x[:4096], x[4096:4096 + 77], x[4096 + 77:]]
+    got = np.concatenate(list(sdr.dcBlockingFilter(chunks)))
+    want, _, _ = ref.dc_blocker(x, 0.0, 0.0)
+    assert np.array_equal(got, want)
+
+
 def test_dc_blocker_bitexact(sdr, ref):
     x = rnd(8192 + 5, False, 11)
     got, fs, fo = sdr.dcBlocker(x, 0.25, -0.5)

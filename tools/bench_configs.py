@@ -64,6 +64,21 @@ def main():
     num = (n - 128) // 8 + 1
     ms = timed(ctx, lambda: L.check(L.lib.sdr_decimate_stream(d.handle, x.ptr, n, y.ptr, num)))
     report("cfg2 decimate-by-8 128-tap complex", ms, n, 9.0, d.last_kernel())
+    # element-wise stages (K4, K5, P4), device resident, through the layer-1 kernels' device entry points
+    nbytes = 2 * n
+    bbuf = ctx.alloc(nbytes)
+    ctx.synth_bytes(bbuf, nbytes)
+    L.lib.sdr_dev_convert_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
+    L.lib.sdr_dev_scale.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_longlong]
+    L.lib.sdr_dev_fm_demod.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_longlong]
+    ms = timed(ctx, lambda: L.check(L.lib.sdr_dev_convert_u8(ctx.h, bbuf.ptr, y.ptr, nbytes)))
+    report("K4 convert u8 IQ -> complex float (per IQ pair)", ms, n, 10.0)
+    ms = timed(ctx, lambda: L.check(L.lib.sdr_dev_scale(ctx.h, 0.2, x.ptr, y.ptr, 2 * n)))
+    report("K5 scale (per float)", ms, 2 * n, 8.0)
+    ms = timed(ctx, lambda: L.check(L.lib.sdr_dev_fm_demod(ctx.h, 0.0, 0.0, x.ptr, y.ptr, n)))
+    report("P4 fmDemod (per complex sample)", ms, n, 12.0)
+    bbuf.free()
+
     # cfg4: the FM chain through connected device pipes, u8 IQ in
     nb = n   # IQ pairs
     raw = ctx.alloc(2 * nb)
