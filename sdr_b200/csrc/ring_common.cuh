@@ -68,15 +68,17 @@ __device__ __forceinline__ int gen_read(uint32_t addr) {
 // matched the phase two generations back -- does the warp back off until it is armed and wait again.
 // GUARD = false when the number of slots is a multiple of the number of warps: then every generation of a slot is
 // consumed by the same warp, in order, and the one-bit parity cannot alias.
+// the rare path lives out of line so that it cannot disturb the register allocation / scheduling of the hot loop
+static __device__ __noinline__ void slot_wait_slow(uint32_t bar, uint32_t gen_addr, int gen) {
+    while (gen_read(gen_addr) < gen) __nanosleep(64);
+    mbar_wait(bar, (gen - 1) & 1);
+}
 template <bool GUARD>
 __device__ __forceinline__ void slot_wait(uint32_t bar, uint32_t gen_addr, int gen) {
     if (!GUARD) { mbar_wait(bar, (gen - 1) & 1); return; }
     const int armed = gen_read(gen_addr);
     mbar_wait(bar, (gen - 1) & 1);
-    if (armed < gen) {
-        while (gen_read(gen_addr) < gen) __nanosleep(64);
-        mbar_wait(bar, (gen - 1) & 1);
-    }
+    if (armed < gen) slot_wait_slow(bar, gen_addr, gen);
 }
 
 // Ring of NS contiguous slots of SLOT_BYTES in shared memory, filled by ONE TMA bulk copy per slot (issued by lane 0
