@@ -96,8 +96,8 @@ int launch_res_r_fast(Ctx *c, int L, int M, int n_taps, const float *d_plain_tap
                       float *d_out, long long num, long long *done, const char **name);
 
 // fused u8 convert + decimate + FM demod of outputs [0, num) of a byte stream (kernels_fm.cu)
-int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, const uint8_t *d_in, long long n_samples, float *d_out,
-                    long long num, float2 *d_bnd, long long bnd_capacity_subtiles, const float2 *d_carry, float2 *d_carry_out,
-                    long long *done, const char **name);
+int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
+                    float *d_out, long long num, float2 *d_bnd, long long bnd_capacity_subtiles, const float2 *d_carry,
+                    float2 *d_carry_out, long long *done, const char **name);
 
 }  // namespace sdr

@@ -23,7 +23,7 @@
 
 namespace sdr {
 
-template <int T, int D, int R>
+template <int T, int D, int R, int NW>
 struct FmCfg {
     static_assert(T % D == 0 && D == 8 && R == 8, "one decimation block = 8 IQ pairs = one 16-byte chunk");
     static constexpr int JB = T / D;
@@ -34,8 +34,8 @@ struct FmCfg {
     static constexpr int SUB_BYTES = 32 * SEG_BYTES;        // 4096 input bytes
     static constexpr int SLOT_BYTES = 32 * SEG_STRIDE;      // 4608
     static constexpr int HALO_SEGS = (JB - 1 + R - 1) / R;  // 2
-    static constexpr int NWARPS = 8;
-    static constexpr int NS = 24;
+    static constexpr int NWARPS = NW;
+    static constexpr int NS = 3 * NW <= 32 ? 3 * NW : 2 * NW;   // 24 slots for 8 warps, 32 for 16
     static constexpr int RING_BYTES = NS * SLOT_BYTES + HALO_SEGS * SEG_STRIDE;
     static constexpr int BAR_OFFSET = ((RING_BYTES + 127) / 128) * 128;
     static constexpr int SMEM_BYTES = BAR_OFFSET + 2 * NS * 8 + 128;
@@ -67,11 +67,14 @@ __device__ __forceinline__ float2 unpack2f(u64 v) {
 // bnd: 2 complex per sub-tile: [2t] = first output of sub-tile t, [2t+1] = last output.  The kernel covers ALL `num`
 // outputs: chunks past the end of the stream are zero-filled (no valid output needs them), stores of the ragged last
 // sub-tile are masked, and the stream's final complex output goes to *carry_out (the next call's carried sample).
-template <int T, int D, int R>
-__global__ void __launch_bounds__(256, 1)
+// SYM: the taps are symmetric (c[k] = c[T-1-k], the usual linear-phase design): only T/2 of them are kept in registers,
+// which halves the register footprint and lets 16 warps (instead of 8) share the SM -- the epilogue is latency bound,
+// so the extra warps are what fills the FP32 pipe.  Same tap values in the same order: bit-identical results.
+template <int T, int D, int R, int NW, bool SYM>
+__global__ void __launch_bounds__(32 * NW, 1)
 k_fm_front_ring(const uint8_t *__restrict__ in, long long n_chunks, float *__restrict__ out, long long num,
                 float2 *__restrict__ bnd, float2 *__restrict__ carry_out, const float *__restrict__ taps, long long n_sub) {
-    typedef FmCfg<T, D, R> C;
+    typedef FmCfg<T, D, R, NW> C;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
@@ -114,9 +117,10 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long n_chunks, float *__res
 
     for (int u = warp; u < C::NS && u <= cnt; u += C::NWARPS) issue_fill(u);
 
-    float tap[T];
+    constexpr int NT = SYM ? T / 2 : T;
+    float tap[NT];
 #pragma unroll
-    for (int k = 0; k < T; k++) tap[k] = __ldg(taps + k);
+    for (int k = 0; k < NT; k++) tap[k] = __ldg(taps + k);
     const u64 k_scale = dup2(0.0078125f), k_bias = dup2(-65537.0f);
 
     for (int u = warp; u < cnt; u += C::NWARPS) {
@@ -144,7 +148,10 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long n_chunks, float *__res
                 const int j = b - r;
                 if (j < 0 || j >= C::JB) continue;
 #pragma unroll
-                for (int p = 0; p < D; p++) acc[r] = ffma2(v[p], dup2(tap[j * D + p]), acc[r]);
+                for (int p = 0; p < D; p++) {
+                    const int k = j * D + p;
+                    acc[r] = ffma2(v[p], dup2(tap[(SYM && k >= T / 2) ? T - 1 - k : k]), acc[r]);
+                }
             }
         }
         // the slot's bytes are in registers: hand it back before the (long) epilogue
@@ -199,34 +206,45 @@ __global__ void __launch_bounds__(256) k_fm_front_fixup(float *__restrict__ out,
 // Fused convert + decimate + demod of outputs [0, num) of a byte stream holding n_samples IQ pairs.  d_carry: previous
 // stream sample (re, im) on the device, read by the fix-up; d_carry_out receives the last decimated complex output;
 // d_bnd: scratch of 2 complex per sub-tile (ceil(num / 256) sub-tiles).  *done = num when the shape has a tuned kernel.
-int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, const uint8_t *d_in, long long n_samples, float *d_out,
-                    long long num, float2 *d_bnd, long long bnd_capacity_subtiles, const float2 *d_carry, float2 *d_carry_out,
-                    long long *done, const char **name) {
+int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
+                    float *d_out, long long num, float2 *d_bnd, long long bnd_capacity_subtiles, const float2 *d_carry,
+                    float2 *d_carry_out, long long *done, const char **name) {
     *done = 0;
     *name = "unfused";
     if (T != 128 || D != 8 || num <= 0) return SDR_OK;
     if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 3) != 0) return SDR_OK;
-    typedef FmCfg<128, 8, 8> C;
     if ((num - 1) * D + T > n_samples) return set_error(SDR_EINVAL, "launch_fm_front: %lld outputs need more than %lld samples", num, n_samples);
-    long long n_sub = (num + C::SUB_OUT - 1) / C::SUB_OUT;
+    const long long n_sub = (num + 255) / 256;
     if (bnd_capacity_subtiles < n_sub) return set_error(SDR_EINVAL, "launch_fm_front: boundary scratch too small");
     SDR_TRY(c->bind());
-    static thread_local int attr_dev = -1;
-    if (attr_dev != c->device) {
-        SDR_CUDA(cudaFuncSetAttribute(k_fm_front_ring<128, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_dev = c->device;
-    }
     int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
-    k_fm_front_ring<128, 8, 8><<<grid, 256, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
+    if (symmetric) {
+        typedef FmCfg<128, 8, 8, 16> C;
+        static thread_local int attr_dev = -1;
+        if (attr_dev != c->device) {
+            SDR_CUDA(cudaFuncSetAttribute(k_fm_front_ring<128, 8, 8, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+            attr_dev = c->device;
+        }
+        k_fm_front_ring<128, 8, 8, 16, true><<<grid, 512, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
+        *name = "fm_front_ring<128,8,8,sym,16w>";
+    } else {
+        typedef FmCfg<128, 8, 8, 8> C;
+        static thread_local int attr_dev = -1;
+        if (attr_dev != c->device) {
+            SDR_CUDA(cudaFuncSetAttribute(k_fm_front_ring<128, 8, 8, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+            attr_dev = c->device;
+        }
+        k_fm_front_ring<128, 8, 8, 8, false><<<grid, 256, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
+        *name = "fm_front_ring<128,8,8>";
+    }
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     long long fg = (n_sub + 255) / 256;
     if (fg > 4LL * c->sm_count) fg = 4LL * c->sm_count;
-    k_fm_front_fixup<<<(int)fg, 256, 0, c->s()>>>(d_out, d_bnd, d_carry, n_sub, C::SUB_OUT);
+    k_fm_front_fixup<<<(int)fg, 256, 0, c->s()>>>(d_out, d_bnd, d_carry, n_sub, 256);
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     *done = num;
-    *name = "fm_front_ring<128,8,8>";
     return SDR_OK;
 }
 

@@ -235,7 +235,7 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     float *carry_in = p->d_last + 2 * p->last_sel, *carry_out = p->d_last + 2 * (p->last_sel ^ 1);
     long long done = 0;
     const char *name = nullptr;
-    SDR_TRY(launch_fm_front(p->ctx, f.T, f.D, f.d_taps, (const uint8_t *)(p->in.p + p->in.rd), have, out, count, (float2 *)p->bnd.p,
+    SDR_TRY(launch_fm_front(p->ctx, f.T, f.D, f.d_taps, f.symmetric, (const uint8_t *)(p->in.p + p->in.rd), have, out, count, (float2 *)p->bnd.p,
                             (long long)(p->bnd.cap / 16), (const float2 *)carry_in, (float2 *)carry_out, &done, &name));
     p->last_kernel = name;
     if (done < count) {

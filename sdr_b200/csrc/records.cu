@@ -54,6 +54,8 @@ int FirRec::create(Ctx *c, bool is_complex, int factor, const float *coeffs, int
         full.assign(coeffs, coeffs + n);
         full.resize(T, 0.0f);
     }
+    symmetric = true;
+    for (int k = 0; k < T / 2; k++) if (memcmp(&full[k], &full[T - 1 - k], sizeof(float)) != 0) { symmetric = false; break; }
     SDR_CUDA(cudaMalloc(&d_taps, sizeof(float) * T));
     SDR_CUDA(cudaMemcpyAsync(d_taps, full.data(), sizeof(float) * T, cudaMemcpyHostToDevice, c->stream));
     // EXACT: the AVX member of the family (CPUID.hs:100-104 picks AVX first)

@@ -20,6 +20,7 @@ struct FirRec {
     int   ex_W = 8, ex_layout = 0, ex_sym = 0, ex_T = 0;
     float *d_ex_taps = nullptr;
     const char *last_kernel = "none";
+    bool  symmetric = false;   // c[k] == c[T-1-k] bit for bit (lets kernels keep half the taps in registers)
     int create(Ctx *c, bool is_complex, int factor, const float *coeffs, int n, int size_multiple, bool sym_half);
     void destroy();
     // y[m] = sum_k c[k] x[first + m*D + k], x = seg.a ++ seg.b (zeros beyond), m < num.  `first` in elements.

@@ -356,6 +356,34 @@ def test_native_resampler_pipe_vs_reference_pipe(sdr, cplx, sizes):
     close(np.concatenate(got), np.concatenate(want))
 
 
+def test_pipe_run_pinned_continuing_stream(sdr, L, ref):
+    """the e2e path of bench.py: sdr_pipe_run with SDR_HOST_PINNED vectors in and out, batching knob set, several passes
+    through one long-lived pipe (the stream continues across calls); every yielded vector against the reference C"""
+    import ctypes as C
+    BUF, n_vecs, passes = 8192, 48, 3
+    taps = synth.windowed_sinc_taps(128, 1 / 16)
+    dec = sdr.cudaDecimatorC(8, taps, sizeMultiple=4)
+    pipe = sdr.pipeFirDecimator(dec, BUF)
+    L.check(L.lib.sdr_pipe_set_batch(pipe.h, 4 * BUF))
+    hin = sdr.PinnedArray(np.float32, 2 * n_vecs * BUF)
+    hout = sdr.PinnedArray(np.float32, 2 * (n_vecs * BUF // 8 + BUF))
+    stream = synth.noise_complex(passes * n_vecs * BUF)
+    got = []
+    n_out = C.c_longlong()
+    for k in range(passes):
+        hin.array[:] = stream[k * n_vecs * BUF:(k + 1) * n_vecs * BUF].view(np.float32)
+        L.check(L.lib.sdr_pipe_run(pipe.h, pipe.h, hin.p, BUF, n_vecs, L.SDR_HOST_PINNED, hout.p, len(hout.array) // 2,
+                                   L.SDR_HOST_PINNED, C.byref(n_out)))
+        assert n_out.value % BUF == 0
+        got.append(hout.array[:2 * n_out.value].view(np.complex64).copy())
+    y = np.concatenate(got)
+    total = (len(stream) - 128) // 8 + 1
+    assert len(y) == (total // BUF) * BUF       # only whole vectors are ever yielded
+    want = ref.decimate("decimateAVXRC", len(y), 8, np.repeat(taps, 2), stream)
+    close(y, want)
+    pipe.close(); hin.free(); hout.free()
+
+
 def test_pipe_precondition_errors(sdr):
     d = sdr.cudaDecimatorC(8, taps_for(128, 1), sizeMultiple=4)
     with pytest.raises(sdr.SdrError) as e:
@@ -403,12 +431,15 @@ def test_fm_chain_connected_pipes_vs_oracle(sdr, port):
 
 @pytest.mark.parametrize("block_out,sizes", [(8192, [16384 * 8] * 6), (1000, [16384, 2 * 3001, 2 * 300, 2 * 9000, 2 * 40000, 2 * 70000]),
                                              (4096, [1 << 22, 1 << 22])])
-def test_fused_fm_frontend_equals_unfused_chain(sdr, port, block_out, sizes):
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_fused_fm_frontend_equals_unfused_chain(sdr, port, block_out, sizes, symmetric):
     """sdr_pipe_fm_frontend == convert >-> firDecimator >-> fmDemod connected stage by stage, BIT FOR BIT (same FIR
     summation order, same discriminator), and both match the oracle chain"""
     ctx = sdr.default_context()
     raw = synth.rand_bytes(sum(sizes))
     t_dec = synth.windowed_sinc_taps(128, 1 / 16)
+    if not symmetric:   # arbitrary taps take the 8-warp kernel that keeps all 128 in registers
+        t_dec = (t_dec * np.linspace(0.5, 1.5, 128)).astype(np.float32)
     dec = sdr.cudaDecimatorC(8, t_dec, sizeMultiple=4)
     fused = sdr.pipeFmFrontEnd(dec, block_out)
     p0 = sdr.pipeConvertU8(ctx)
@@ -428,6 +459,7 @@ def test_fused_fm_frontend_equals_unfused_chain(sdr, port, block_out, sizes):
             b.append(p2.pop())
     assert len(a) == len(b) and len(a) >= 1 and all(len(v) == block_out for v in a)
     assert used_fused
+    assert ("sym" in sdr._lib.lib.sdr_pipe_last_kernel(fused.h).decode()) == symmetric
     A, B = np.concatenate(a), np.concatenate(b)
     assert np.array_equal(A, B), f"{int((A != B).sum())} of {len(A)} differ, first at {int(np.argmax(A != B))}"
     # oracle chain on a prefix (CPU cost)
