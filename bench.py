@@ -184,6 +184,17 @@ def run_gpu(args, rank, world, local_rank, dist):
     d_out = ctx.alloc(8 * max(plan.out_count, 1) + 256)
     ctx.synth_noise(d_in, 2 * plan.in_count, first_float=2 * plan.in_begin)
     ctx.sync()
+    halo = "none"
+    if world > 1:
+        halo = "nccl send/recv per pass"
+        if args.halo == "peer":
+            dist.barrier()   # every chunk complete before a neighbour may read it
+            try:
+                comm.share_chunks(d_in.ptr)
+                halo = "peer memory (CUDA IPC over NVLink), read in place by the boundary launch"
+            except sdr_b200.SdrError as e:
+                if rank == 0:
+                    print(f"peer-memory halo unavailable ({e}); using NCCL", file=sys.stderr)
 
     def barrier():
         ctx.sync()
@@ -264,7 +275,7 @@ def run_gpu(args, rank, world, local_rank, dist):
                            "taps": TAPS, "decimation": FACTOR, "buffer": BUF, "samples": n,
                            "l2": "inputs exceed L2 (per-GPU chunk %.0f MiB in + %.0f MiB out vs 126 MB L2)" % (
                                8 * plan.in_count / 2 ** 20, 8 * plan.out_count / 2 ** 20),
-                           "sharding": "single GPU" if world == 1 else f"{world} overlapping chunks, NCCL halo of {TAPS - FACTOR} samples per boundary",
+                           "sharding": "single GPU" if world == 1 else f"{world} overlapping chunks, halo of {TAPS - FACTOR} samples per boundary via {halo}",
                            "arithmetic": "fp32 FMA, taps in increasing order; parity vs reference AVX path <= 1e-5 of output scale (tests/test_gpu_parity.py)",
                            "output_checksum": "%016x" % csum},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_total, "clocks": clocks}
@@ -369,6 +380,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2_STREAM, help="stream length (default 2^28, the headline workload)")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "peer"],
+                    help="multi-GPU halo transport: NCCL send/recv per pass (default) or in-place peer-memory reads")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -312,6 +312,13 @@ typedef struct sdr_comm sdr_comm_t;
 int sdr_comm_unique_id(unsigned char id[SDR_COMM_ID_BYTES]);
 int sdr_comm_create(sdr_ctx_t *ctx, const unsigned char id[SDR_COMM_ID_BYTES], int world, int rank, sdr_comm_t **c);
 int sdr_comm_destroy(sdr_comm_t *c);
+/* Optional peer-memory transport for the halo (collective over the communicator): every rank passes the base address
+ * of the sdr_dev_alloc allocation holding its chunk; CUDA IPC handles are exchanged with ncclAllGather and each rank
+ * maps its right neighbour's chunk.  sdr_decimate_sharded on that same d_in then reads the T-D halo samples in place
+ * from the neighbour's HBM over NVLink inside its boundary launch (no per-pass NCCL kernel).  The caller guarantees
+ * the neighbour's chunk is complete before a pass starts. */
+int sdr_comm_share_chunks(sdr_comm_t *c, const void *d_chunk_base);
+int sdr_comm_peer_halo_active(const sdr_comm_t *c, const void *d_in);
 /* one pass of the sharded decimator: interior outputs on the ctx stream, halo exchange (ncclSend of my first
  * `halo` samples to rank-1 / ncclRecv from rank+1) on a side stream, boundary outputs after the halo lands.
  * d_in: this rank's resident chunk (plan.in_count samples); d_out: plan.out_count outputs. */

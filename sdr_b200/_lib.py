@@ -154,6 +154,8 @@ _sig("sdr_shard_plan", _LL, _I, _I, _I, _I, C.POINTER(ShardPlan))
 _sig("sdr_comm_unique_id", _P)
 _sig("sdr_comm_create", _P, _P, _I, _I, c_void_pp)
 _sig("sdr_comm_destroy", _P)
+_sig("sdr_comm_share_chunks", _P, _P)
+_sig("sdr_comm_peer_halo_active", _P, _P)
 _sig("sdr_decimate_sharded", _P, _P, C.POINTER(ShardPlan), _P, _P)
 _sig("sdr_synth_noise", _P, _P, _LL, _LL, C.c_uint32)
 _sig("sdr_synth_bytes", _P, _P, _LL, _LL, C.c_uint32)

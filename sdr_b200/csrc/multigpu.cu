@@ -12,6 +12,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <vector>
+
 namespace sdr {
 
 struct NcclApi {
@@ -23,6 +25,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -46,6 +49,7 @@ static int nccl_api(NcclApi **out) {
             SDR_SYM(GroupEnd, "ncclGroupEnd");
             SDR_SYM(Send, "ncclSend");
             SDR_SYM(Recv, "ncclRecv");
+            SDR_SYM(AllGather, "ncclAllGather");
             SDR_SYM(GetErrorString, "ncclGetErrorString");
 #undef SDR_SYM
             if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send &&
@@ -76,6 +80,9 @@ struct sdr_comm {
     int world = 1, rank = 0;
     void *d_halo = nullptr;
     size_t halo_bytes = 0;
+    // peer transport: the right neighbour's registered chunk, mapped into this process with CUDA IPC
+    const void *my_base = nullptr;   // the allocation this rank registered
+    void *peer_base = nullptr;       // rank+1's allocation as seen from here (nullptr: NCCL transport)
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
 };
 
@@ -146,10 +153,50 @@ int sdr_comm_destroy(sdr_comm_t *c) {
     cudaStreamSynchronize(c->ctx->side);
     if (c->comm) c->api->CommDestroy(c->comm);
     if (c->d_halo) cudaFree(c->d_halo);
+    if (c->peer_base) cudaIpcCloseMemHandle(c->peer_base);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     delete c;
     return SDR_OK;
+}
+
+// Collective.  Every rank passes the BASE address of the device allocation that holds its chunk (as returned by
+// sdr_dev_alloc).  The CUDA IPC handles travel by ncclAllGather; each rank maps its right neighbour's allocation.
+// Afterwards sdr_decimate_sharded on that same d_in reads the T-D halo samples straight out of the neighbour's HBM over
+// NVLink inside the boundary launch: no NCCL kernel per pass, no rendezvous, no SMs set aside.  The caller guarantees
+// that the neighbour's chunk is complete before a pass starts (e.g. a barrier after producing it).
+int sdr_comm_share_chunks(sdr_comm_t *c, const void *d_chunk_base) {
+    if (!c || !d_chunk_base) return set_error(SDR_EINVAL, "sdr_comm_share_chunks: bad argument");
+    Ctx *ctx = c->ctx;
+    SDR_TRY(ctx->bind());
+    if (c->peer_base) { cudaIpcCloseMemHandle(c->peer_base); c->peer_base = nullptr; }
+    c->my_base = nullptr;
+    if (c->world == 1) return SDR_OK;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t mine;
+    SDR_CUDA(cudaIpcGetMemHandle(&mine, const_cast<void *>(d_chunk_base)));
+    unsigned char *d_all = nullptr;
+    SDR_CUDA(cudaMalloc(&d_all, 64 * (size_t)(c->world + 1)));
+    SDR_CUDA(cudaMemcpyAsync(d_all + 64 * (size_t)c->world, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    ncclResult_t r = c->api->AllGather(d_all + 64 * (size_t)c->world, d_all, 64, ncclChar, c->comm, ctx->stream);
+    if (r != ncclSuccess) { cudaFree(d_all); return set_error(SDR_ENCCL, "ncclAllGather of IPC handles failed: %s", c->api->GetErrorString(r)); }
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    SDR_CUDA(cudaMemcpyAsync(all.data(), d_all, 64 * (size_t)c->world, cudaMemcpyDeviceToHost, ctx->stream));
+    SDR_CUDA(cudaStreamSynchronize(ctx->stream));
+    SDR_CUDA(cudaFree(d_all));
+    if (c->rank + 1 < c->world) {
+        void *peer = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&peer, all[c->rank + 1], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle(right neighbour)", __FILE__, __LINE__);
+        c->peer_base = peer;
+    }
+    c->my_base = d_chunk_base;
+    return SDR_OK;
+}
+
+// 1 when sdr_decimate_sharded on this d_in would use the peer-memory transport
+int sdr_comm_peer_halo_active(const sdr_comm_t *c, const void *d_in) {
+    return c && c->my_base && c->my_base == d_in ? 1 : 0;
 }
 
 int sdr_decimate_sharded(sdr_decimator_t *d, sdr_comm_t *c, const sdr_shard_t *plan, const void *d_in, void *d_out) {
@@ -166,6 +213,29 @@ int sdr_decimate_sharded(sdr_decimator_t *d, sdr_comm_t *c, const sdr_shard_t *p
     const size_t eb = elem_bytes(r.cplx);
     const long long local0 = plan->out_begin * plan->factor - plan->in_begin;
     bool exchange = false;
+    const bool peer = plan->world > 1 && c->my_base && c->my_base == d_in;
+    if (peer) {
+        // halo read in place from the neighbour's HBM: tuned kernel over the resident sub-tiles on the main stream (all
+        // SMs), ragged end + boundary windows in one generic launch on the side stream with seg.b = the neighbour's chunk
+        if (plan->halo > 0 && !c->peer_base) return set_error(SDR_EPRECOND, "sdr_decimate_sharded: no mapped right neighbour");
+        long long done = 0;
+        const char *kernel = r.last_kernel;
+        SDR_CUDA(cudaEventRecord(c->ev_ready, ctx->stream));
+        SDR_TRY(r.run_tuned(d_in, plan->in_count, local0, d_out, plan->out_interior, &done));
+        if (done > 0) kernel = r.last_kernel;
+        if (plan->out_count > done) {
+            SDR_CUDA(cudaStreamWaitEvent(ctx->side, c->ev_ready, 0));
+            Seg2 seg = {d_in, plan->in_count, c->peer_base, plan->halo};
+            ctx->override_st = ctx->side;
+            int rc = r.run(seg, local0 + done * plan->factor, (char *)d_out + (size_t)done * eb, plan->out_count - done, false);
+            ctx->override_st = nullptr;
+            SDR_TRY(rc);
+            SDR_CUDA(cudaEventRecord(c->ev_halo, ctx->side));
+            SDR_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_halo, 0));
+        }
+        r.last_kernel = kernel;
+        return SDR_OK;
+    }
     if (plan->world > 1) {
         // what my left neighbour needs from the head of my chunk
         sdr_shard_t left;

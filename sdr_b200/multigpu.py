@@ -26,6 +26,13 @@ class Comm:
         L.check(L.lib.sdr_comm_create(ctx.h, buf, world, rank, C.byref(h)))
         self.h, self.ctx, self.world, self.rank = h, ctx, world, rank
 
+    def share_chunks(self, d_chunk_base):
+        """collective: map the right neighbour's chunk (CUDA IPC) so the halo is read in place over NVLink"""
+        L.check(L.lib.sdr_comm_share_chunks(self.h, d_chunk_base))
+
+    def peer_halo_active(self, d_in) -> bool:
+        return bool(L.lib.sdr_comm_peer_halo_active(self.h, d_in))
+
     def close(self):
         if self.h:
             L.lib.sdr_comm_destroy(self.h)

@@ -75,6 +75,11 @@ def main():
     d_in = ctx.alloc(8 * plan.in_count + 64)
     d_out = ctx.alloc(8 * max(plan.out_count, 1) + 64)
     ctx.synth_noise(d_in, 2 * plan.in_count, first_float=2 * plan.in_begin)
+    if mode == "gpu-peer":
+        ctx.sync()
+        dist.barrier()                      # every rank's chunk is complete before anyone reads a neighbour's
+        comm.share_chunks(d_in.ptr)
+        assert comm.peer_halo_active(d_in.ptr)
     for _ in range(3):   # repeated passes reuse the halo buffer and events
         multigpu.decimate_sharded(dec, comm, plan, d_in.ptr, d_out.ptr)
     ctx.sync()
@@ -104,7 +109,7 @@ def main():
         want = ctx.checksum32(y, 2 * total_out)
         got = sum(p[0] for p in parts) & 0xffffffffffffffff
         assert got == want, (hex(got), hex(want))
-        print("MG_OK gpu", world, n)
+        print("MG_OK", mode, world, n)
     comm.close()
     dist.destroy_process_group()
 

@@ -30,3 +30,14 @@ def test_sharded_halo_exchange_nccl(world):
         pytest.skip(f"needs {world} GPUs")
     _launch(world, "gpu", 24, 0)
     _launch(world, "gpu", 20, 4096 + 24)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_peer_memory_halo(world):
+    """halo read in place from the neighbour's HBM (CUDA IPC + NVLink) instead of an NCCL exchange"""
+    import sdr_b200
+    if sdr_b200.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _launch(world, "gpu-peer", 24, 0)
+    _launch(world, "gpu-peer", 20, 4096 + 24)
