@@ -249,6 +249,8 @@ int sdr_resample_cross(sdr_resampler_t *r, sdr_resampler_dat_t *dat, int count, 
 /* Layer 3: Pipes.  A pipe consumes whole input vectors (push = the Pipe's `await`) and produces output vectors   */
 /* of exactly block_size_out elements (pop = `yield`), re-blocking like advanceOutBuf (Filter.hs:516-523).        */
 /* On the device the stream is kept contiguous (tail carried in HBM), so there is no crossover case.              */
+/* FIR stages launch lazily: only when the new outputs complete at least one output vector (sdr_pipe_set_batch     */
+/* raises that threshold); since vectors are only ever yielded whole this is invisible except in timing.          */
 /* ---------------------------------------------------------------------------------------------------------- */
 typedef struct sdr_pipe sdr_pipe_t;
 

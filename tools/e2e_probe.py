@@ -1,5 +1,8 @@
+"""PCIe probe behind bench.py's e2e number (measurement tool): sdr_pipe_run from pinned host vectors at several batch
+sizes, next to plain / chunked / interleaved cudaMemcpy rates on the same box."""
 import sys, os, ctypes as C, time
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, sdr_b200, synth
 from sdr_b200 import _lib as L
 ctx = sdr_b200.default_context()
