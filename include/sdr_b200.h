@@ -158,6 +158,19 @@ int fmDemodCuda(int num, float lastRe, float lastIm, const float *in, float *out
 int sdr_dev_convert_u8(sdr_ctx_t *ctx, const uint8_t *d_in, float *d_out, long long n_bytes);   /* convert.c:15 */
 int sdr_dev_scale(sdr_ctx_t *ctx, float factor, const float *d_in, float *d_out, long long n);  /* scale.c:15   */
 int sdr_dev_fm_demod(sdr_ctx_t *ctx, float last_re, float last_im, const float *d_in, float *d_out, long long n); /* Demod.hs:32 */
+/* dcBlocker (filter.c:152) on device buffers; d_final2 receives (finalSample, finalOutput).  Vectors of at least
+ * 65536 samples are evaluated chunk-parallel by speculation + verification (sdr_b200/csrc/dc_spec.cuh) -- still
+ * bit-exact for any input; shorter, unaligned or in-place calls run the serial one-lane kernel. */
+int sdr_dev_dc_blocker(sdr_ctx_t *ctx, float last_sample, float last_output, const float *d_in, float *d_out, long long n,
+                       float *d_final2);
+/* Tuning of that speculation for this context: chunk length in samples (0 = automatic), cheap and exact warm-up
+ * lengths (-1 = default 6144 / 4096), shortest vector that takes the parallel path (-1 = default).  Results are
+ * bit-exact for every setting; short warm-ups only make chunks miss and be repaired serially. */
+int sdr_dc_blocker_tuning(sdr_ctx_t *ctx, int chunk, int cheap_warmup, int exact_warmup, long long min_parallel);
+/* Counters since the context's first parallel call: stats[0] parallel calls, [1] chunks, [2] chunks repaired,
+ * [3] samples rewritten by repairs; *last_parallel = whether the most recent dcBlocker call took the parallel path.
+ * Synchronises the ctx stream. */
+int sdr_dc_blocker_stats(sdr_ctx_t *ctx, long long stats[4], int *last_parallel);
 
 /* ---------------------------------------------------------------------------------------------------------- */
 /* Verification entry points: SDR_ARITH_EXACT arithmetic of ONE named reference variant, HOST pointers.           */

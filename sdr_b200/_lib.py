@@ -104,6 +104,12 @@ _sig("convertCudaBladeRFTransmit", _I, _P, _P)
 _sig("scaleCuda", _I, _F, _P, _P)
 _sig("dcBlockerCuda", _I, _F, _F, _f32p, _f32p, _P, _P)
 _sig("fmDemodCuda", _I, _F, _F, _P, _P)
+_sig("sdr_dev_convert_u8", _P, _P, _P, _LL)
+_sig("sdr_dev_scale", _P, _F, _P, _P, _LL)
+_sig("sdr_dev_fm_demod", _P, _F, _F, _P, _P, _LL)
+_sig("sdr_dev_dc_blocker", _P, _F, _F, _P, _P, _LL, _P)
+_sig("sdr_dc_blocker_tuning", _P, _I, _I, _I, _LL)
+_sig("sdr_dc_blocker_stats", _P, C.POINTER(_LL), C.POINTER(_I))
 
 _sig("sdr_filter_create", _P, _I, _P, _I, _I, c_void_pp)
 _sig("sdr_filter_create_sym", _P, _I, _P, _I, c_void_pp)

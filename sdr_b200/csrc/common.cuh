@@ -41,7 +41,12 @@ struct Ctx {
     void  *d_stage_in = nullptr; size_t d_stage_in_bytes = 0;
     void  *d_stage_out = nullptr; size_t d_stage_out_bytes = 0;
     void  *d_flush = nullptr; size_t d_flush_bytes = 0;
+    // dcBlocker speculation (kernels_dc.cu): per-chunk scratch + counters, tuning overrides (0 / -1 = default)
+    void  *d_dc_scratch = nullptr; size_t d_dc_scratch_bytes = 0; bool dc_scratch_regrown = false;
+    int    dc_chunk = 0, dc_k1 = -1, dc_k2 = -1, dc_last_parallel = 0;
+    long long dc_min_parallel = -1;
     int ensure_stage(size_t in_bytes, size_t out_bytes);
+    int ensure_dc_scratch(size_t bytes);
     int bind() const;  // cudaSetDevice
 };
 

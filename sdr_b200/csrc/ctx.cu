@@ -56,6 +56,13 @@ int Ctx::ensure_stage(size_t in_bytes, size_t out_bytes) {
     return SDR_OK;
 }
 
+int Ctx::ensure_dc_scratch(size_t bytes) {
+    const size_t before = d_dc_scratch_bytes;
+    SDR_TRY(grow(&d_dc_scratch, &d_dc_scratch_bytes, bytes, false));
+    if (d_dc_scratch_bytes != before) dc_scratch_regrown = true;   // fresh block: the counters in its head are garbage
+    return SDR_OK;
+}
+
 // Per-thread default context used by the reference-signature one-shot entry points (layer 1).
 Ctx *default_ctx(int *status) {
     static thread_local Ctx *c = nullptr;
@@ -128,6 +135,7 @@ int sdr_ctx_destroy(sdr_ctx_t *ctx) {
     if (c->d_stage_in) cudaFree(c->d_stage_in);
     if (c->d_stage_out) cudaFree(c->d_stage_out);
     if (c->d_flush) cudaFree(c->d_flush);
+    if (c->d_dc_scratch) cudaFree(c->d_dc_scratch);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     cudaStreamDestroy(c->stream);

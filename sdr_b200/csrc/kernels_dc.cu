@@ -1,0 +1,193 @@
+// kernels_dc.cu -- dcBlocker (c_sources/filter.c:152-161) / dcBlockingFilter (hs_sources/SDR/Filter.hs:730-739) on the
+// device: the serial one-lane kernel for short vectors and the speculative chunk-parallel evaluation of dc_spec.cuh for
+// long ones.  Both are bit-exact; see dc_spec.cuh for why the parallel one is.
+#include "common.cuh"
+#include "dc_spec.cuh"
+
+#include <cstdlib>
+
+namespace sdr {
+
+#define SDR_LAUNCH_CHECK(c)                       \
+    do {                                          \
+        (c)->launches++;                          \
+        SDR_CUDA(cudaGetLastError());             \
+    } while (0)
+
+// Serial form.  Each y[n] depends on the ROUNDED y[n-1]: one lane evaluates the recurrence, the warp only streams the
+// data through shared memory in coalesced 1024-sample pieces.
+__global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last_output, const float *__restrict__ state_in,
+                                                   const float *__restrict__ in, float *__restrict__ out, long long n,
+                                                   float *__restrict__ final2) {
+    __shared__ float buf[1024];
+    if (state_in) { last_sample = state_in[0]; last_output = state_in[1]; }   // streaming form: state carried on the device
+    for (long long base = 0; base < n; base += 1024) {
+        int m = (int)((n - base) < 1024 ? (n - base) : 1024);
+        for (int i = threadIdx.x; i < m; i += 32) buf[i] = in[base + i];
+        __syncwarp();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < m; i++) {
+                float x = buf[i];
+                last_output = dc_exact(x, last_sample, last_output);
+                last_sample = x;
+                buf[i] = last_output;
+            }
+        }
+        __syncwarp();
+        for (int i = threadIdx.x; i < m; i += 32) out[base + i] = buf[i];
+        __syncwarp();
+    }
+    if (threadIdx.x == 0) { final2[0] = last_sample; final2[1] = last_output; }
+}
+
+// Speculative pass: one lane per chunk (neighbouring lanes own neighbouring chunks; a lane reads and writes whole
+// 32-byte sectors, two 16-byte accesses each).
+template <bool VEC> __global__ void __launch_bounds__(128) k_dc_spec(DcArgs A) {
+    const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (c < A.chunks) dc_chunk<VEC>(A, c);
+}
+
+// Check + repair.  All threads compare spec[c] with fin[c-1] and build the bitmap of missed chunks; if there is none
+// (the usual case) the kernel only publishes the final state, otherwise thread 0 repairs them in stream order.
+__global__ void __launch_bounds__(1024) k_dc_repair(DcArgs A) {
+    int any = 0;
+    for (long long c0 = (long long)(threadIdx.x / 32) * 32; c0 < A.chunks; c0 += blockDim.x) {
+        const long long c = c0 + (threadIdx.x & 31);
+        const bool miss = c > 0 && c < A.chunks && dc_missed(A, c, A.fin[c - 1]);
+        const unsigned m = __ballot_sync(0xffffffffu, miss);
+        if ((threadIdx.x & 31) == 0) A.fail_bits[c0 / 32] = m;
+        any |= (m != 0);
+    }
+    any = __syncthreads_or(any);   // also orders the bitmap writes before thread 0's reads
+    if (threadIdx.x != 0) return;
+    if (any) { dc_repair(A); return; }
+    A.stats[0] += 1; A.stats[1] += (unsigned long long)A.chunks;
+    if (A.final2) {
+        const float fs = A.in[A.n - 1], fo = dc_float(A.fin[A.chunks - 1]);
+        A.final2[0] = fs; A.final2[1] = fo;
+    }
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    int v = atoi(e);
+    return v >= 0 ? v : dflt;
+}
+
+// Tuning (dc_spec.cuh): chunk length 0 = automatic (about 384 lanes per SM, 1024..16384 samples), warm-up lengths.
+// The environment variables exist for measurement sweeps and for tests that force speculation to miss.
+static void dc_tuning(const Ctx *c, long long n, int *ch, int *k1, int *k2) {
+    int want = c->dc_chunk > 0 ? c->dc_chunk : env_int("SDR_B200_DC_CHUNK", 0);
+    *k1 = c->dc_k1 >= 0 ? c->dc_k1 : env_int("SDR_B200_DC_K1", 6144);
+    *k2 = c->dc_k2 >= 0 ? c->dc_k2 : env_int("SDR_B200_DC_K2", 4096);
+    if (want <= 0) {
+        long long lanes = (long long)c->sm_count * 384;
+        long long per = (n + lanes - 1) / lanes;
+        if (per < 1024) per = 1024;
+        if (per > 16384) per = 16384;
+        want = (int)per;
+    }
+    *ch = (want + 7) & ~7;
+    *k1 = (*k1 + 7) & ~7;
+    *k2 = (*k2 + 7) & ~7;
+}
+
+static bool overlap(const void *a, const void *b, size_t bytes) {
+    const char *p = (const char *)a, *q = (const char *)b;
+    return p < q + bytes && q < p + bytes;
+}
+
+static int dc_run(Ctx *c, float last_sample, float last_output, const float *d_state, const float *d_in, float *d_out, long long n,
+                  float *d_final2) {
+    if (n <= 0) return SDR_OK;
+    SDR_TRY(c->bind());
+    const long long min_parallel = c->dc_min_parallel >= 0 ? c->dc_min_parallel : 65536;
+    const bool aligned4 = (((uintptr_t)d_in | (uintptr_t)d_out) & 3) == 0;
+    if (n < min_parallel || !aligned4 || overlap(d_in, d_out, (size_t)n * 4)) {   // in-place calls keep the serial kernel
+        k_dc_blocker<<<1, 32, 0, c->s()>>>(last_sample, last_output, d_state, d_in, d_out, n, d_final2);
+        SDR_LAUNCH_CHECK(c);
+        c->dc_last_parallel = 0;
+        return SDR_OK;
+    }
+    DcArgs A;
+    A.in = d_in; A.out = d_out; A.n = n;
+    A.last_sample = last_sample; A.last_output = last_output; A.state_in = d_state;
+    dc_tuning(c, n, &A.ch, &A.k1, &A.k2);
+    A.chunks = (n + A.ch - 1) / A.ch;
+    const size_t words = (size_t)((A.chunks + 31) / 32);
+    const size_t need = 64 + (size_t)A.chunks * 8 + words * 4;
+    SDR_TRY(c->ensure_dc_scratch(need));
+    char *base = (char *)c->d_dc_scratch;
+    if (c->dc_scratch_regrown) {
+        SDR_CUDA(cudaMemsetAsync(base, 0, 64, c->s()));   // the counters start at zero (and restart when the block moves)
+        c->dc_scratch_regrown = false;
+    }
+    A.stats = (unsigned long long *)base;
+    A.spec = (uint32_t *)(base + 64);
+    A.fin = A.spec + A.chunks;
+    A.fail_bits = A.fin + A.chunks;
+    A.final2 = d_final2;
+    const bool vec = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
+    const int  grid = (int)((A.chunks + 127) / 128);
+    if (vec) k_dc_spec<true><<<grid, 128, 0, c->s()>>>(A);
+    else     k_dc_spec<false><<<grid, 128, 0, c->s()>>>(A);
+    SDR_LAUNCH_CHECK(c);
+    k_dc_repair<<<1, 1024, 0, c->s()>>>(A);
+    SDR_LAUNCH_CHECK(c);
+    c->dc_last_parallel = 1;
+    return SDR_OK;
+}
+
+int launch_dc_blocker(Ctx *c, float last_sample, float last_output, const float *d_in, float *d_out, long long n,
+                      float *d_final2) {
+    return dc_run(c, last_sample, last_output, nullptr, d_in, d_out, n, d_final2);
+}
+// d_state: (lastSample, lastOutput) on the device, read before and updated after the block (dcBlockingFilter's pMapAccum)
+int launch_dc_blocker_carry(Ctx *c, float *d_state, const float *d_in, float *d_out, long long n) {
+    return dc_run(c, 0.0f, 0.0f, d_state, d_in, d_out, n, d_state);
+}
+
+}  // namespace sdr
+
+using namespace sdr;
+
+extern "C" {
+
+int sdr_dev_dc_blocker(sdr_ctx_t *ctx, float last_sample, float last_output, const float *d_in, float *d_out, long long n,
+                       float *d_final2) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || n < 0 || (n && (!d_in || !d_out)) || !d_final2) return set_error(SDR_EINVAL, "sdr_dev_dc_blocker: bad argument");
+    if (n == 0) {
+        const float st[2] = {last_sample, last_output};
+        SDR_TRY(c->bind());
+        SDR_CUDA(cudaMemcpyAsync(d_final2, st, 8, cudaMemcpyHostToDevice, c->s()));
+        SDR_CUDA(cudaStreamSynchronize(c->s()));
+        return SDR_OK;
+    }
+    return launch_dc_blocker(c, last_sample, last_output, d_in, d_out, n, d_final2);
+}
+
+int sdr_dc_blocker_tuning(sdr_ctx_t *ctx, int chunk, int cheap_warmup, int exact_warmup, long long min_parallel) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return set_error(SDR_EINVAL, "sdr_dc_blocker_tuning: null context");
+    if (chunk > 0 && chunk < 8) return set_error(SDR_EINVAL, "sdr_dc_blocker_tuning: chunk %d < 8", chunk);
+    c->dc_chunk = chunk; c->dc_k1 = cheap_warmup; c->dc_k2 = exact_warmup; c->dc_min_parallel = min_parallel;
+    return SDR_OK;
+}
+
+int sdr_dc_blocker_stats(sdr_ctx_t *ctx, long long stats[4], int *last_parallel) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !stats) return set_error(SDR_EINVAL, "sdr_dc_blocker_stats: bad argument");
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (last_parallel) *last_parallel = c->dc_last_parallel;
+    if (!c->d_dc_scratch) return SDR_OK;
+    SDR_TRY(c->bind());
+    SDR_CUDA(cudaStreamSynchronize(c->s()));
+    unsigned long long h[4];
+    SDR_CUDA(cudaMemcpy(h, c->d_dc_scratch, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; i++) stats[i] = (long long)h[i];
+    return SDR_OK;
+}
+
+}  // extern "C"

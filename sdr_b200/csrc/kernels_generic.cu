@@ -429,49 +429,7 @@ int launch_fm_demod_carry(Ctx *c, const float *d_last, const float *d_in, float 
     return launch_fm_demod_any(c, 0.0f, 0.0f, d_last, d_in, d_out, n);
 }
 
-// dcBlocker (filter.c:152-161): y[n] = (x[n] - x[n-1]) + 0.997 * y[n-1]; the difference is a float subtraction, the
-// product and sum are evaluated in double (0.997 is a double literal) and rounded to float on the store.  Each y[n]
-// depends on the ROUNDED y[n-1], so the recurrence is evaluated serially by one lane (bit-exact); the warp only
-// streams the data through shared memory in coalesced 1024-sample chunks.
-__global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last_output, const float *__restrict__ state_in,
-                                                   const float *__restrict__ in, float *__restrict__ out, long long n,
-                                                   float *__restrict__ final2) {
-    __shared__ float buf[1024];
-    if (state_in) { last_sample = state_in[0]; last_output = state_in[1]; }   // streaming form: state carried on the device
-    for (long long base = 0; base < n; base += 1024) {
-        int m = (int)((n - base) < 1024 ? (n - base) : 1024);
-        for (int i = threadIdx.x; i < m; i += 32) buf[i] = in[base + i];
-        __syncwarp();
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < m; i++) {
-                float x = buf[i];
-                double acc = __dadd_rn((double)__fsub_rn(x, last_sample), __dmul_rn(0.997, (double)last_output));
-                last_output = __double2float_rn(acc);
-                last_sample = x;
-                buf[i] = last_output;
-            }
-        }
-        __syncwarp();
-        for (int i = threadIdx.x; i < m; i += 32) out[base + i] = buf[i];
-        __syncwarp();
-    }
-    if (threadIdx.x == 0) { final2[0] = last_sample; final2[1] = last_output; }
-}
-int launch_dc_blocker(Ctx *c, float last_sample, float last_output, const float *d_in, float *d_out, long long n,
-                      float *d_final2) {
-    SDR_TRY(c->bind());
-    k_dc_blocker<<<1, 32, 0, c->s()>>>(last_sample, last_output, nullptr, d_in, d_out, n, d_final2);
-    SDR_LAUNCH_CHECK(c);
-    return SDR_OK;
-}
-// d_state: (lastSample, lastOutput) on the device, read before and updated after the block (dcBlockingFilter's pMapAccum)
-int launch_dc_blocker_carry(Ctx *c, float *d_state, const float *d_in, float *d_out, long long n) {
-    if (n <= 0) return SDR_OK;
-    SDR_TRY(c->bind());
-    k_dc_blocker<<<1, 32, 0, c->s()>>>(0.0f, 0.0f, d_state, d_in, d_out, n, d_state);
-    SDR_LAUNCH_CHECK(c);
-    return SDR_OK;
-}
+// dcBlocker / dcBlockingFilter: kernels_dc.cu
 
 // ---------------------------------------------------------------------------------------------------------------
 // synthetic streams (counter-based, keyed on the GLOBAL element index) and measurement helpers

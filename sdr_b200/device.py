@@ -60,6 +60,21 @@ class Context:
     def synth_bytes(self, buf, n_bytes, first_byte=0, seed=0x5D2B200, offset_bytes=0):
         L.check(L.lib.sdr_synth_bytes(self.h, C.c_void_p(buf.ptr.value + offset_bytes), n_bytes, first_byte, seed))
 
+    def dc_blocker(self, d_in, d_out, n, d_final2, last_sample=0.0, last_output=0.0):
+        """dcBlocker (filter.c:152-161) on device buffers (ctypes pointers); enqueue-only"""
+        L.check(L.lib.sdr_dev_dc_blocker(self.h, last_sample, last_output, d_in, d_out, n, d_final2))
+
+    def dc_tuning(self, chunk=0, cheap_warmup=-1, exact_warmup=-1, min_parallel=-1):
+        """speculation parameters of the chunk-parallel dcBlocker (csrc/dc_spec.cuh); the defaults restore automatic"""
+        L.check(L.lib.sdr_dc_blocker_tuning(self.h, chunk, cheap_warmup, exact_warmup, min_parallel))
+
+    def dc_stats(self):
+        """(parallel calls, chunks, chunks repaired, samples rewritten by repairs), last call took the parallel path"""
+        st = (C.c_longlong * 4)()
+        par = C.c_int()
+        L.check(L.lib.sdr_dc_blocker_stats(self.h, st, C.byref(par)))
+        return tuple(int(v) for v in st), bool(par.value)
+
     def close(self):
         if self.h:
             L.lib.sdr_ctx_destroy(self.h)

@@ -1,0 +1,36 @@
+// TEST INFRASTRUCTURE: runs the product's dcBlocker speculation (sdr_b200/csrc/dc_spec.cuh -- the very functions the
+// CUDA kernels k_dc_spec / k_dc_repair execute, compiled here for the host) one chunk after the other, so the chunk
+// planning, warm-up, verification and repair logic is checked bit for bit against the oracle without a GPU.
+// Built by tests/test_dc_speculation.py with g++ -O2 -ffp-contract=off; never linked into libsdr_b200.so.
+#include "../../sdr_b200/csrc/dc_spec.cuh"
+
+#include <vector>
+
+using namespace sdr;
+
+extern "C" int emul_dc_blocker(const float *in, float *out, long long n, float last_sample, float last_output, int ch,
+                               int k1, int k2, int vec, int reverse_chunks, float *final2, unsigned long long *stats) {
+    if (n <= 0 || ch < 8 || (ch & 7) || (k1 & 7) || (k2 & 7)) return 1;
+    DcArgs A;
+    A.in = in; A.out = out; A.n = n;
+    A.last_sample = last_sample; A.last_output = last_output; A.state_in = nullptr;
+    A.ch = ch; A.k1 = k1; A.k2 = k2;
+    A.chunks = (n + ch - 1) / ch;
+    std::vector<uint32_t> spec(A.chunks, 0xdeadbeefu), fin(A.chunks, 0xdeadbeefu), bits((A.chunks + 31) / 32, 0);
+    A.spec = spec.data(); A.fin = fin.data(); A.fail_bits = bits.data();
+    A.stats = stats; A.final2 = final2;
+    // the lanes of the kernel run in no particular order
+    for (long long i = 0; i < A.chunks; i++) {
+        const long long c = reverse_chunks ? A.chunks - 1 - i : i;
+        if (vec) dc_chunk<true>(A, c); else dc_chunk<false>(A, c);
+    }
+    bool any = false;
+    for (long long c = 1; c < A.chunks; c++)
+        if (dc_missed(A, c, A.fin[c - 1])) { bits[c / 32] |= 1u << (c % 32); any = true; }
+    if (any) dc_repair(A);
+    else {
+        stats[0] += 1; stats[1] += (unsigned long long)A.chunks;
+        if (final2) { final2[0] = in[n - 1]; final2[1] = dc_float(A.fin[A.chunks - 1]); }
+    }
+    return 0;
+}

@@ -266,6 +266,108 @@ def test_dc_blocker_bitexact(sdr, ref):
     assert np.array_equal(got, want) and fs == ws and fo == wo
 
 
+def _dc_dev(ctx, x, s0=0.0, o0=0.0, in_off=0, out_off=0):
+    """sdr_dev_dc_blocker on device buffers placed in_off / out_off floats past a 256-byte aligned allocation"""
+    n = len(x)
+    d_in, d_out, d_fin = ctx.alloc(4 * n + 64), ctx.alloc(4 * n + 64), ctx.alloc(8)
+    d_in.upload(x, 4 * in_off)
+    ctx.dc_blocker(d_in.at(4 * in_off), d_out.at(4 * out_off), n, d_fin.ptr, s0, o0)
+    got, fin = d_out.to_host(np.float32, n, 4 * out_off), d_fin.to_host(np.float32, 2)
+    for b in (d_in, d_out, d_fin):
+        b.free()
+    return got, fin
+
+
+def _dc_delta(before, after):
+    return tuple(a - b for a, b in zip(after, before))
+
+
+def test_dc_blocker_parallel_bitexact(sdr, ctx, ref):
+    """long vectors take the speculative chunk-parallel path (csrc/dc_spec.cuh): bit-exact, and with the default warm-up
+    no chunk of a noise stream needs a repair"""
+    x = rnd(1_000_003, False, 21)
+    want, ws, wo = ref.dc_blocker(x, 0.25, -0.5)
+    st0, _ = ctx.dc_stats()
+    got, fin = _dc_dev(ctx, x, 0.25, -0.5)
+    st1, par = ctx.dc_stats()
+    assert par, "a 1M-sample vector must take the parallel path"
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(fin.view(np.uint32), np.array([ws, wo], np.float32).view(np.uint32))
+    calls, chunks, repaired, _ = _dc_delta(st0, st1)
+    assert calls == 1 and chunks >= 60 and repaired == 0, (calls, chunks, repaired)
+    # the host-pointer entry point of layer 1 goes the same way
+    got2, fs, fo = sdr.dcBlocker(x, 0.25, -0.5)
+    assert np.array_equal(got2.view(np.uint32), want.view(np.uint32)) and fs == ws and fo == wo
+    # 4-byte aligned device pointers: scalar-access instantiation
+    got3, fin3 = _dc_dev(ctx, x[:300_001], 0.25, -0.5, in_off=1, out_off=3)
+    want3, ws3, wo3 = ref.dc_blocker(x[:300_001], 0.25, -0.5)
+    assert ctx.dc_stats()[1]
+    assert np.array_equal(got3.view(np.uint32), want3.view(np.uint32)) and fin3[1] == wo3 and fin3[0] == ws3
+
+
+def test_dc_blocker_parallel_repairs(ctx, ref):
+    """speculation that misses (warm-up far too short; constant input parked on a denormal fixed point) is repaired
+    serially: still bit-exact"""
+    x = (3.0 * rnd(400_000, False, 22) + 1.0).astype(np.float32)
+    want, ws, wo = ref.dc_blocker(x, 0.0, 7.0)
+    try:
+        for chunk, k1, k2, lo in ((4096, 0, 8, 80), (512, 0, 0, 700), (2048, 6144, 512, 1)):
+            ctx.dc_tuning(chunk, k1, k2, 0)
+            st0, _ = ctx.dc_stats()
+            got, fin = _dc_dev(ctx, x, 0.0, 7.0)
+            st1, par = ctx.dc_stats()
+            assert par
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (chunk, k1, k2)
+            assert fin[0] == ws and fin[1] == wo
+            assert _dc_delta(st0, st1)[2] >= lo, (chunk, k1, k2, _dc_delta(st0, st1))
+        ctx.dc_tuning(2048, 1024, 1024, 0)
+        c = np.full(150_000, 0.5, np.float32)
+        wantc, _, woc = ref.dc_blocker(c, 0.0, 0.0)
+        gotc, finc = _dc_dev(ctx, c)
+        assert np.array_equal(gotc.view(np.uint32), wantc.view(np.uint32)) and finc[1] == woc
+        assert 0 < abs(float(woc)) < 1e-42
+        # ragged lengths through the parallel path (min_parallel = 0)
+        ctx.dc_tuning(64, 64, 512, 0)
+        for n in (1, 7, 9, 1025, 4099):
+            w, _, wo_n = ref.dc_blocker(x[:n], 0.1, 0.2)
+            g, f = _dc_dev(ctx, x[:n], 0.1, 0.2)
+            assert np.array_equal(g.view(np.uint32), w.view(np.uint32)) and f[1] == wo_n, n
+    finally:
+        ctx.dc_tuning()
+
+
+def test_dc_blocking_filter_pipe_long_vectors(sdr, ctx, ref):
+    """dcBlockingFilter with vectors long enough for the parallel path: (lastSample, lastOutput) carried on the device
+    from one vector to the next"""
+    x = rnd(3 * 131072 + 70_000, False, 23)
+    cuts = [0, 131072, 131072 + 70_000, 131072 + 70_000 + 100, len(x)]
+    chunks = [x[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    got = np.concatenate(list(sdr.dcBlockingFilter(chunks, ctx)))
+    want, _, _ = ref.dc_blocker(x, 0.0, 0.0)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_dc_blocker_full_size_parallel_equals_serial(ctx):
+    """size-independent property at 2^25 samples: the chunk-parallel evaluation and the serial kernel (forced by
+    min_parallel) write the same words (checksum of the device buffers)"""
+    n = 1 << 25
+    d_in, d_out, d_fin = ctx.alloc(4 * n), ctx.alloc(4 * n), ctx.alloc(8)
+    ctx.synth_noise(d_in, n)
+    try:
+        ctx.dc_blocker(d_in.ptr, d_out.ptr, n, d_fin.ptr)
+        assert ctx.dc_stats()[1]
+        par = (ctx.checksum32(d_out, n), d_fin.to_host(np.uint32, 2).tolist())
+        ctx.dc_tuning(0, -1, -1, 1 << 40)
+        ctx.dc_blocker(d_in.ptr, d_out.ptr, n, d_fin.ptr)
+        assert not ctx.dc_stats()[1]
+        ser = (ctx.checksum32(d_out, n), d_fin.to_host(np.uint32, 2).tolist())
+        assert par == ser
+    finally:
+        ctx.dc_tuning()
+        for b in (d_in, d_out, d_fin):
+            b.free()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # layer 2: record closures under the reference's own state machine; layer 3: native pipes vs the flat stream
 # ---------------------------------------------------------------------------------------------------------------
