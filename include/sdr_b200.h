@@ -301,6 +301,23 @@ int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs);
  * connected behind it) into `out` back to back, then sdr_pipe_sync.  *n_out = elements written (<= out_capacity). */
 int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_len, long long n_vecs, int in_mem,
                  void *out, long long out_capacity, int out_mem, long long *n_out);
+/* Producer / consumer edges on file descriptors, the steps either side of the path:
+ *   SDR.Serialize.fromHandle n h (Serialize.hs:82-83)  -- stream mode: every vector is exactly vec_len elements read from
+ *       in_fd (blocking until complete; a shorter vector only at end of file), until end of file or max_vecs (0 = no limit);
+ *   SDR.NetworkStream.udpSource sock size (NetworkStream.hs:28-35) -- SDR_IO_DATAGRAM_IN: one read() = one vector of up
+ *       to vec_len elements, max_vecs required;
+ *   SDR.Serialize.toHandle (Serialize.hs:78-79) -- every vector `sink` yields is written to out_fd as raw elements
+ *       (out_fd < 0: discarded); SDR_IO_DATAGRAM_OUT writes one vector per write() (udpSink, NetworkStream.hs:37-42).
+ * read() lands directly in a page-locked ring (two halves of ~8 MiB: one is filled while the other is copied to the
+ * device), vectors are pushed as SDR_HOST_PINNED.  A short last vector that violates a FIR stage's minimum length
+ * returns SDR_EPRECOND after everything before it has been processed and written (the reference asserts there). */
+enum { SDR_IO_DATAGRAM_IN = 1, SDR_IO_DATAGRAM_OUT = 2 };
+typedef struct {
+    long long vectors_in, elements_in, vectors_out, elements_out;
+    double    read_seconds, write_seconds;   /* time spent blocked in read() / write() */
+} sdr_io_stats_t;
+int sdr_pipe_run_fd(sdr_pipe_t *p, sdr_pipe_t *sink, int in_fd, long long vec_len, long long max_vecs, int out_fd, int flags,
+                    sdr_io_stats_t *stats);
 /* connect: everything `src` yields is pushed into `dst` device-to-device without touching the host (>->) */
 int sdr_pipe_connect(sdr_pipe_t *src, sdr_pipe_t *dst);
 

@@ -11,4 +11,4 @@ from .filter import (Decimator, Filter, NativePipe, Resampler, cudaDecimatorC, c
 from .util import (complexFloatToInterleavedIQSigned2048, dcBlocker, dcBlockingFilter, fmDemod, pipeDcBlocker, fmDemodVec,  # noqa: F401
                    interleavedIQSigned2048ToFloat, interleavedIQUnsignedByteToFloat, pipeConvertU8, pipeFmDemod, pipeFmFrontEnd,
                    pipeScale, scaleFast)
-from . import multigpu  # noqa: F401
+from . import multigpu, serialize  # noqa: F401

@@ -52,6 +52,15 @@ class ShardPlan(C.Structure):
                 ("rank", C.c_int)]
 
 
+class IoStats(C.Structure):
+    """sdr_io_stats_t"""
+    _fields_ = [("vectors_in", C.c_longlong), ("elements_in", C.c_longlong), ("vectors_out", C.c_longlong),
+                ("elements_out", C.c_longlong), ("read_seconds", C.c_double), ("write_seconds", C.c_double)]
+
+
+SDR_IO_DATAGRAM_IN, SDR_IO_DATAGRAM_OUT = 1, 2
+
+
 class ResamplerDat(C.Structure):
     """sdr_resampler_dat_t: the Resampler record's existential state (group, offset), Filter.hs:424"""
     _fields_ = [("group", C.c_int), ("offset", C.c_int)]
@@ -155,6 +164,7 @@ _sig("sdr_pipe_sync", _P)
 _sig("sdr_pipe_set_batch", _P, _LL)
 _sig("sdr_pipe_next_len", _P, C.POINTER(_LL))
 _sig("sdr_pipe_run", _P, _P, _P, _LL, _LL, _I, _P, _LL, _I, C.POINTER(_LL))
+_sig("sdr_pipe_run_fd", _P, _P, _I, _LL, _LL, _I, _I, C.POINTER(IoStats))
 
 _sig("sdr_shard_plan", _LL, _I, _I, _I, _I, C.POINTER(ShardPlan))
 _sig("sdr_comm_unique_id", _P)

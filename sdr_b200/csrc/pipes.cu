@@ -12,10 +12,15 @@
 // Outputs are re-blocked into vectors of exactly block_size_out elements like advanceOutBuf (Filter.hs:516-523).
 #include "records.cuh"
 
+#include <cerrno>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <deque>
+#include <vector>
+
+#include <unistd.h>
 
 namespace sdr {
 
@@ -616,6 +621,148 @@ int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_
                 std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_issued).count());
     *n_out = written;
     return SDR_OK;
+}
+
+// ---- producers / consumers on file descriptors ------------------------------------------------------------------------
+namespace {
+
+// one vector for fromHandle (Serialize.hs:82-83: PB.hGet blocks until `want` bytes or end of file) or for udpSource
+// (NetworkStream.hs:33-35: one recv = one vector); returns bytes read, 0 at end of input, -1 on error
+long long read_vector(int fd, char *dst, size_t want, bool datagram) {
+    size_t got = 0;
+    while (got < want) {
+        ssize_t r = ::read(fd, dst + got, want - got);
+        if (r < 0) { if (errno == EINTR) continue; return -1; }
+        if (r == 0) break;
+        got += (size_t)r;
+        if (datagram) break;
+    }
+    return (long long)got;
+}
+bool write_all(int fd, const char *src, size_t bytes) {
+    while (bytes) {
+        ssize_t w = ::write(fd, src, bytes);
+        if (w < 0) { if (errno == EINTR) continue; return false; }
+        src += w; bytes -= (size_t)w;
+    }
+    return true;
+}
+double seconds_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+struct FdRun {
+    char *ring = nullptr, *obuf = nullptr;
+    size_t half_bytes = 0, obuf_bytes = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    ~FdRun() {
+        if (ring) cudaFreeHost(ring);
+        if (obuf) cudaFreeHost(obuf);
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+    }
+};
+
+// pop every complete vector of `sink` and write it to out_fd (toHandle, Serialize.hs:78-79; udpSink, NetworkStream.hs:37-42)
+int drain_to_fd(sdr_pipe *sink, FdRun &R, int out_fd, bool datagram_out, sdr_io_stats_t *st) {
+    std::vector<long long> lens;
+    long long total = 0;
+    if (is_fir_kind(sink->kind)) {
+        long long nb = (long long)(sink->fifo.size() / sink->out_eb) / sink->block_out;
+        for (long long i = 0; i < nb; i++) lens.push_back(sink->block_out);
+        total = nb * sink->block_out;
+    } else {
+        for (long long n : sink->vec_lens) { lens.push_back(n); total += n; }
+    }
+    if (lens.empty()) return SDR_OK;
+    const size_t bytes = (size_t)total * sink->out_eb;
+    if (bytes > R.obuf_bytes) {
+        if (R.obuf) { SDR_CUDA(cudaFreeHost(R.obuf)); R.obuf = nullptr; R.obuf_bytes = 0; }
+        size_t cap = (size_t)1 << 20;
+        while (cap < bytes) cap *= 2;
+        SDR_CUDA(cudaHostAlloc((void **)&R.obuf, cap, cudaHostAllocDefault));
+        R.obuf_bytes = cap;
+    }
+    long long written = 0;
+    SDR_TRY(drain(sink, R.obuf, (long long)(R.obuf_bytes / sink->out_eb), SDR_HOST_PINNED, &written));
+    // the copy rides the side stream (FIR kinds) or the main stream (element-wise kinds): wait for it, not for the
+    // launches queued behind it
+    if (sink->d2h_outstanding) SDR_CUDA(cudaEventSynchronize(sink->ev_out_done));
+    else SDR_CUDA(cudaStreamSynchronize(sink->ctx->stream));
+    st->vectors_out += (long long)lens.size();
+    st->elements_out += written;
+    if (out_fd < 0) return SDR_OK;
+    auto t0 = std::chrono::steady_clock::now();
+    bool ok = true;
+    if (datagram_out) {
+        const char *q = R.obuf;
+        for (long long n : lens) { ok = ok && write_all(out_fd, q, (size_t)n * sink->out_eb); q += (size_t)n * sink->out_eb; }
+    } else {
+        ok = write_all(out_fd, R.obuf, (size_t)written * sink->out_eb);
+    }
+    st->write_seconds += seconds_since(t0);
+    if (!ok) return set_error(SDR_EINVAL, "sdr_pipe_run_fd: write to descriptor %d failed: %s", out_fd, strerror(errno));
+    return SDR_OK;
+}
+
+}  // namespace
+
+int sdr_pipe_run_fd(sdr_pipe_t *p, sdr_pipe_t *sink, int in_fd, long long vec_len, long long max_vecs, int out_fd, int flags,
+                    sdr_io_stats_t *stats) {
+    if (!p || !sink || in_fd < 0 || vec_len <= 0 || max_vecs < 0)
+        return set_error(SDR_EINVAL, "sdr_pipe_run_fd: bad argument");
+    const bool dgram_in = flags & SDR_IO_DATAGRAM_IN, dgram_out = flags & SDR_IO_DATAGRAM_OUT;
+    if (dgram_in && max_vecs == 0)
+        return set_error(SDR_EINVAL, "sdr_pipe_run_fd: a datagram source never ends, max_vecs must be given");
+    sdr_io_stats_t local = {0, 0, 0, 0, 0.0, 0.0};
+    sdr_io_stats_t *st = stats ? stats : &local;
+    *st = local;
+    SDR_TRY(p->ctx->bind());
+    struct BoundGuard { BoundGuard() { g_bound = true; } ~BoundGuard() { g_bound = false; } } bound_guard;
+    FdRun R;
+    const size_t vec_bytes = (size_t)vec_len * p->in_eb;
+    // page-locked staging ring of two halves: read() lands directly in DMA-able memory; while one half is being
+    // copied to the device the other one is being filled
+    size_t per_half = ((size_t)8 << 20) / vec_bytes;
+    if (per_half < 1) per_half = 1;
+    R.half_bytes = per_half * vec_bytes;
+    SDR_CUDA(cudaHostAlloc((void **)&R.ring, 2 * R.half_bytes, cudaHostAllocDefault));
+    for (auto &e : R.ev) SDR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+    bool used[2] = {false, false};
+    int half = 0;
+    size_t fill = 0;
+    int deferred = SDR_OK;
+    for (long long v = 0; max_vecs == 0 || v < max_vecs; v++) {
+        if (fill + vec_bytes > R.half_bytes) {
+            SDR_TRY(flush_pending(p));
+            SDR_CUDA(cudaEventRecord(R.ev[half], p->ctx->stream));
+            used[half] = true;
+            half ^= 1; fill = 0;
+            if (used[half]) SDR_CUDA(cudaEventSynchronize(R.ev[half]));   // its copies to the device have finished
+        }
+        char *dst = R.ring + (size_t)half * R.half_bytes + fill;
+        auto t0 = std::chrono::steady_clock::now();
+        long long got = read_vector(in_fd, dst, vec_bytes, dgram_in);
+        st->read_seconds += seconds_since(t0);
+        if (got < 0) return set_error(SDR_EINVAL, "sdr_pipe_run_fd: read from descriptor %d failed: %s", in_fd, strerror(errno));
+        if (got == 0) break;
+        if ((size_t)got % p->in_eb)
+            return set_error(SDR_EINVAL, "sdr_pipe_run_fd: %lld bytes read are not a whole number of %zu-byte elements", got, p->in_eb);
+        const long long n = got / (long long)p->in_eb;
+        int s = pipe_push_any(p, dst, n, SDR_HOST_PINNED);
+        if (s == SDR_EPRECOND && (size_t)got < vec_bytes && !dgram_in) { deferred = s; break; }   // short last vector: the reference's assert
+        SDR_TRY(s);
+        fill += (size_t)got;
+        st->vectors_in++; st->elements_in += n;
+        SDR_TRY(drain_to_fd(sink, R, out_fd, dgram_out, st));
+        if ((size_t)got < vec_bytes && !dgram_in) break;   // end of file inside the vector
+    }
+    for (sdr_pipe *q = p; q; q = q->downstream) {
+        if (is_fir_kind(q->kind)) { SDR_TRY(process_fir(q, true)); SDR_TRY(forward(q)); }
+        if (q == sink) break;
+    }
+    SDR_TRY(drain_to_fd(sink, R, out_fd, dgram_out, st));
+    SDR_TRY(sdr_pipe_sync(p));
+    return deferred;
 }
 
 int sdr_pipe_connect(sdr_pipe_t *src, sdr_pipe_t *dst) {

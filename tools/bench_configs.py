@@ -110,6 +110,28 @@ def main():
     report("cfg4 fused front end alone (u8 IQ -> convert -> decimate-by-8 -> fmDemod)", ms, nb, 2.5, L.lib.sdr_pipe_last_kernel(fe.h).decode())
     fe.close()
 
+    # recorded-IQ replay: fromHandle (Serialize.hs:82) on a tmpfs file -> pinned ring -> fused front end, output discarded
+    try:
+        path = "/dev/shm/sdr_b200_iq.u8"
+        nrep = min(nb, 1 << 28)            # IQ pairs in the file (2 bytes each)
+        host = raw.to_host(np.uint8, 2 * nrep)
+        host.tofile(path)
+        del host
+        import time
+        for vec_bytes in (16384, 1 << 20):
+            fe2 = sdr_b200.pipeFmFrontEnd(d, 8192)
+            L.check(L.lib.sdr_pipe_set_batch(fe2.h, 1 << 21))
+            with open(path, "rb") as fi:
+                t0 = time.perf_counter()
+                st = sdr_b200.serialize.runHandles(fe2, fe2, vec_bytes, fi, None)
+                dt = time.perf_counter() - t0
+            report(f"file replay (tmpfs) -> fromHandle {vec_bytes}-byte vectors -> fused FM front end (wall clock; read() {st.read_seconds:.3f} s)",
+                   dt * 1e3, st.elements_in // 2, 2.5, L.lib.sdr_pipe_last_kernel(fe2.h).decode())
+            fe2.close()
+        os.remove(path)
+    except Exception as e:   # measurement aid only
+        print(json.dumps({"config": "file replay", "error": str(e)}), flush=True)
+
     def build_chain(fused):
         if fused:
             head = sdr_b200.pipeFmFrontEnd(d, 8192)
@@ -133,17 +155,19 @@ def main():
                     pass
         return head, p5, stages
 
-    for fused in (False, True):
+    for fused, chunk in ((False, 1 << 25), (True, 1 << 25), (True, 1 << 26), (True, 1 << 27), (True, 1 << 28)):
+        if chunk > 2 * nb:
+            continue
         head, tail, stages = build_chain(fused)
         n_out = C.c_longlong()
-        chunk = 1 << 25   # bytes per push (device memory): 16M IQ pairs
+        # chunk = bytes per push (device memory): 2^25 = 16M IQ pairs
 
         def run():
             L.check(L.lib.sdr_pipe_run(head.h, tail.h, raw.ptr, chunk, (2 * nb) // chunk, L.SDR_DEVICE, y.ptr, 2 * n, L.SDR_DEVICE,
                                        C.byref(n_out)))
         ms = timed(ctx, run, steps=5, warmup=2)
         kern = L.lib.sdr_pipe_last_kernel(head.h).decode() if fused else ""
-        report("cfg4 FM chain u8 IQ -> audio, device pipes, " + ("fused front end" if fused else "stage by stage"), ms, nb, 2.15, kern)
+        report("cfg4 FM chain u8 IQ -> audio, device pipes, " + ("fused front end" if fused else "stage by stage") + f", {chunk >> 20} MiB pushes", ms, nb, 2.15, kern)
         for p in stages:
             p.close()
 
