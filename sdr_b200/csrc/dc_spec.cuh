@@ -64,24 +64,44 @@ SDR_HD float dc_float(uint32_t u) {
 #endif
 }
 
+// Exact float -> double widening with integer operations (normal numbers and zeros; denormals, infinities and NaN take
+// the conversion instruction).  On the device the float<->double conversions run on the XU pipe at about one warp
+// instruction per 23 cycles and were the bound of the first version of the speculative kernel (ncu: XU 101 % busy, three
+// conversions per step); the recurrence itself needs only the one rounding double -> float.  Checked against (double)f
+// for all 2^32 bit patterns (tests/test_dc_speculation.py::test_widen_exhaustive_sample).
+SDR_HD double dc_widen(float f) {
+    const uint32_t b = dc_bits(f);
+    const uint32_t mag = b & 0x7fffffffu;
+    if (mag != 0 && mag - 0x00800000u >= 0x7f000000u) return (double)f;   // denormal, inf, NaN
+    uint32_t hi = (mag >> 3) + 0x38000000u;   // exponent rebias 127 -> 1023, top 20 mantissa bits
+    hi = (mag == 0 ? 0u : hi) | (b & 0x80000000u);
+    const uint32_t lo = b << 29;              // low 3 mantissa bits
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    const uint64_t u = ((uint64_t)hi << 32) | lo;
+    double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+
 // one exact step: returns y[n] from x[n], x[n-1], y[n-1] (filter.c:155: float difference, double product and sum,
 // one rounding to float on the assignment)
 SDR_HD float dc_exact(float x, float last_sample, float last_output) {
 #if defined(__CUDA_ARCH__)
-    return __double2float_rn(__dadd_rn((double)__fsub_rn(x, last_sample), __dmul_rn(0.997, (double)last_output)));
+    return __double2float_rn(__dadd_rn(dc_widen(__fsub_rn(x, last_sample)), __dmul_rn(0.997, dc_widen(last_output))));
 #else
     volatile float  d = x - last_sample;                 // volatile: no contraction, no excess precision
-    volatile double p = 0.997 * (double)last_output;
-    volatile double s = (double)d + p;
+    volatile double p = 0.997 * dc_widen(last_output);
+    volatile double s = dc_widen(d) + p;
     return (float)s;
 #endif
 }
-// one cheap step on a double state (warm-up only; never stored)
-SDR_HD double dc_cheap(float x, float last_sample, double a) {
+// one cheap step on a double state (warm-up only; never stored): xd, ld = the sample and its predecessor widened
+SDR_HD double dc_cheap(double xd, double ld, double a) {
 #if defined(__CUDA_ARCH__)
-    return __fma_rn(0.997, a, (double)__fsub_rn(x, last_sample));
+    return __fma_rn(0.997, a, __dsub_rn(xd, ld));
 #else
-    return __builtin_fma(0.997, a, (double)(x - last_sample));
+    return __builtin_fma(0.997, a, xd - ld);
 #endif
 }
 
@@ -123,34 +143,40 @@ template <bool VEC> SDR_HD void dc_chunk(const DcArgs &A, long long c) {
     float  l = (w == 0) ? s0 : A.in[w - 1];
     double a = (w == 0) ? (double)o0 : 0.0;
 
+    // the next two groups are always in flight before the current one is evaluated (a group is ~500 cycles of
+    // dependent arithmetic, a DRAM access under load rather more)
     long long pos = w;
-    DcGroup   cur;
+    DcGroup   cur = DcGroup(), nx1 = DcGroup(), nx2;
     if (pos < full_end) cur = dc_load8<VEC>(A.in, pos);
+    if (pos + 8 < full_end) nx1 = dc_load8<VEC>(A.in, pos + 8);
+    double ld = dc_widen(l);
     for (; pos < e0; pos += 8) {
-        DcGroup nxt = cur;
-        if (pos + 8 < full_end) nxt = dc_load8<VEC>(A.in, pos + 8);
+        nx2 = nx1;
+        if (pos + 16 < full_end) nx2 = dc_load8<VEC>(A.in, pos + 16);
 #pragma unroll
-        for (int i = 0; i < 8; i++) { a = dc_cheap(cur.v[i], l, a); l = cur.v[i]; }
-        cur = nxt;
+        for (int i = 0; i < 8; i++) { const double xd = dc_widen(cur.v[i]); a = dc_cheap(xd, ld, a); ld = xd; }
+        l = cur.v[7];
+        cur = nx1; nx1 = nx2;
     }
     float o = (float)a;   // exact when nothing was warmed up cheaply (a == o0); (float) is round-to-nearest on both sides
     for (; pos < b0; pos += 8) {
-        DcGroup nxt = cur;
-        if (pos + 8 < full_end) nxt = dc_load8<VEC>(A.in, pos + 8);
+        nx2 = nx1;
+        if (pos + 16 < full_end) nx2 = dc_load8<VEC>(A.in, pos + 16);
 #pragma unroll
         for (int i = 0; i < 8; i++) { o = dc_exact(cur.v[i], l, o); l = cur.v[i]; }
-        cur = nxt;
+        cur = nx1; nx1 = nx2;
     }
     if (c > 0) A.spec[c] = dc_bits(o);
     for (; pos < full_end; pos += 8) {
-        DcGroup nxt = cur;
-        if (pos + 8 < full_end) nxt = dc_load8<VEC>(A.in, pos + 8);
+        nx2 = nx1;
+        if (pos + 16 < full_end) nx2 = dc_load8<VEC>(A.in, pos + 16);
         DcGroup y;
 #pragma unroll
         for (int i = 0; i < 8; i++) { o = dc_exact(cur.v[i], l, o); l = cur.v[i]; y.v[i] = o; }
         dc_store8<VEC>(A.out, pos, y);
-        cur = nxt;
+        cur = nx1; nx1 = nx2;
     }
+#pragma unroll 1
     for (; pos < b1; pos++) {   // ragged end of the stream (last chunk only)
         const float x = A.in[pos];
         o = dc_exact(x, l, o); l = x;

@@ -34,3 +34,14 @@ extern "C" int emul_dc_blocker(const float *in, float *out, long long n, float l
     }
     return 0;
 }
+
+// dc_widen against the compiler's own float -> double conversion over bit patterns first, first + step, ... (step 1 = all 2^32)
+extern "C" unsigned long long emul_dc_widen_mismatches(unsigned long long first, unsigned long long step) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = first; i < (1ull << 32); i += step) {
+        const float  f = dc_float((uint32_t)i);
+        const double want = (double)f, got = dc_widen(f);
+        if (memcmp(&want, &got, 8) != 0) bad++;
+    }
+    return bad;
+}

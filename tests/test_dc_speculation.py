@@ -64,6 +64,14 @@ def check(lib, port, x, s0=0.0, o0=0.0, **kw):
     return stats
 
 
+def test_widen_exhaustive_sample(emul):
+    """dc_widen (integer float -> double widening, the conversion the device code avoids) == (double)f for every one of
+    the 2^32 bit patterns"""
+    emul.emul_dc_widen_mismatches.restype = C.c_ulonglong
+    emul.emul_dc_widen_mismatches.argtypes = [C.c_ulonglong, C.c_ulonglong]
+    assert emul.emul_dc_widen_mismatches(0, 1) == 0
+
+
 def noise(n, seed=1, scale=1.0, offset=0.0):
     return (np.random.default_rng(seed).standard_normal(n) * scale + offset).astype(np.float32)
 
