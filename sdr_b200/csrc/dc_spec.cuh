@@ -41,7 +41,7 @@ struct DcArgs {
     long long    n;
     float        last_sample, last_output;   // state before in[0] ...
     const float *state_in;                   // ... or, when non-null, (lastSample, lastOutput) read from here
-    int          ch, k1, k2;                 // chunk length, cheap warm-up, exact warm-up: multiples of 8
+    int          ch, k1, k2;                 // chunk length, cheap warm-up, exact warm-up: multiples of 32
     long long    chunks;                     // ceil(n / ch)
     uint32_t    *spec, *fin;                 // [chunks] value reached before the chunk / at its end (float bits)
     uint32_t    *fail_bits;                  // [(chunks + 31) / 32] bitmap of chunks whose speculation missed
@@ -105,84 +105,131 @@ SDR_HD double dc_cheap(double xd, double ld, double a) {
 #endif
 }
 
-struct DcGroup { float v[8]; };
+// ---- one lane's walk over its chunk, in tiles of 32 samples ----------------------------------------------------------
+// A lane visits positions [b0 - K1 - K2, b1) of the stream in 32-sample tiles (chunk and warm-up lengths are multiples
+// of 32, so a tile lies in exactly one phase and every lane of a warp is in the same phase at the same time):
+//   cheap warm-up  [b0 - K1 - K2, b0 - K2)   double state, one DFMA per sample
+//   exact warm-up  [b0 - K2, b0)             the reference's arithmetic, nothing stored
+//   owned          [b0, b1)                  the reference's arithmetic, outputs stored
+// Tiles before the start of the stream are skipped; the lane then starts at position 0 from the true state.
+#define SDR_DC_TILE 32
 
-template <bool VEC> SDR_HD DcGroup dc_load8(const float *in, long long pos) {
-    DcGroup g;
-    if (VEC) {   // in is 16-byte aligned and pos a multiple of 8
-        const float4 a = *reinterpret_cast<const float4 *>(in + pos), b = *reinterpret_cast<const float4 *>(in + pos + 4);
-        g.v[0] = a.x; g.v[1] = a.y; g.v[2] = a.z; g.v[3] = a.w; g.v[4] = b.x; g.v[5] = b.y; g.v[6] = b.z; g.v[7] = b.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) g.v[i] = in[pos + i];
-    }
-    return g;
+struct DcLane {
+    long long b0, b1;    // owned range
+    long long pos;       // position of the next tile (negative: before the stream start)
+    float     l, o;      // previous sample, current output (exact phases)
+    double    a, ld;     // cheap phase: state and previous sample, widened
+    bool      started;
+};
+
+SDR_HD void dc_lane_init(const DcArgs &A, long long c, DcLane &L) {
+    L.b0 = c * A.ch;
+    L.b1 = (L.b0 + A.ch < A.n) ? L.b0 + A.ch : A.n;
+    if (c >= A.chunks) L.b1 = L.b0;   // no such chunk: never active
+    L.pos = L.b0 - A.k1 - A.k2;
+    L.l = 0.0f; L.o = 0.0f; L.a = 0.0; L.ld = 0.0;
+    L.started = false;
 }
-template <bool VEC> SDR_HD void dc_store8(float *out, long long pos, const DcGroup &g) {
-    if (VEC) {
-        *reinterpret_cast<float4 *>(out + pos)     = make_float4(g.v[0], g.v[1], g.v[2], g.v[3]);
-        *reinterpret_cast<float4 *>(out + pos + 4) = make_float4(g.v[4], g.v[5], g.v[6], g.v[7]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) out[pos + i] = g.v[i];
+SDR_HD long long dc_lane_tiles(const DcArgs &A) { return (A.k1 + A.k2 + A.ch) / SDR_DC_TILE; }
+
+// One tile.  `rd.get4(q)` delivers samples in[pos + 4q .. pos + 4q + 3], `wr.put4(q, v)` takes the four outputs of the
+// same positions (owned tiles only; positions past the end of the stream carry the last value and are masked by the
+// writer).  Returns true when the tile produced outputs.  The accessors keep only four samples live at a time: on the
+// device they are shared-memory rows, on the host (and in the unaligned kernel) plain memory.
+template <typename Rd, typename Wr>
+SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, Wr &wr) {
+    const long long pos = L.pos;
+    L.pos += SDR_DC_TILE;
+    if (pos < 0 || pos >= L.b1) return false;
+    if (!L.started) {
+        L.started = true;
+        if (pos == 0) {   // the true state before in[0]
+            L.l = A.state_in ? A.state_in[0] : A.last_sample;
+            L.o = A.state_in ? A.state_in[1] : A.last_output;
+            L.a = dc_widen(L.o);
+        } else {          // speculation: y = 0 at the start of the warm-up
+            L.l = A.in[pos - 1];
+            L.o = 0.0f; L.a = 0.0;
+        }
+        L.ld = dc_widen(L.l);
     }
+    if (pos == L.b0 && c > 0) A.spec[c] = dc_bits(L.o);   // what this lane believes y[b0 - 1] to be
+    if (pos < L.b0 - A.k2) {
+        double a = L.a, ld = L.ld;
+        float  last = L.l;
+#pragma unroll
+        for (int q = 0; q < SDR_DC_TILE / 4; q++) {
+            const float4 v = rd.get4(q);
+            double xd;
+            xd = dc_widen(v.x); a = dc_cheap(xd, ld, a); ld = xd;
+            xd = dc_widen(v.y); a = dc_cheap(xd, ld, a); ld = xd;
+            xd = dc_widen(v.z); a = dc_cheap(xd, ld, a); ld = xd;
+            xd = dc_widen(v.w); a = dc_cheap(xd, ld, a); ld = xd;
+            last = v.w;
+        }
+        L.a = a; L.ld = ld; L.l = last;
+        L.o = (float)a;   // round-to-nearest on host and device; the exact phase continues from here
+        return false;
+    }
+    float l = L.l, o = L.o;
+    if (pos < L.b0) {
+#pragma unroll
+        for (int q = 0; q < SDR_DC_TILE / 4; q++) {
+            const float4 v = rd.get4(q);
+            o = dc_exact(v.x, l, o); o = dc_exact(v.y, v.x, o); o = dc_exact(v.z, v.y, o); o = dc_exact(v.w, v.z, o);
+            l = v.w;
+        }
+        L.l = l; L.o = o;
+        return false;
+    }
+    const int m = (L.b1 - pos < SDR_DC_TILE) ? (int)(L.b1 - pos) : SDR_DC_TILE;   // < 32 only at the end of the stream
+#pragma unroll
+    for (int q = 0; q < SDR_DC_TILE / 4; q++) {
+        const float4 v = rd.get4(q);
+        float4       y;
+        if (4 * q + 0 < m) { o = dc_exact(v.x, l, o); l = v.x; } y.x = o;
+        if (4 * q + 1 < m) { o = dc_exact(v.y, l, o); l = v.y; } y.y = o;
+        if (4 * q + 2 < m) { o = dc_exact(v.z, l, o); l = v.z; } y.z = o;
+        if (4 * q + 3 < m) { o = dc_exact(v.w, l, o); l = v.w; } y.w = o;
+        wr.put4(q, y);
+    }
+    L.l = l; L.o = o;
+    if (pos + SDR_DC_TILE >= L.b1) A.fin[c] = dc_bits(o);
+    return true;
 }
 
-// Speculative evaluation of chunk c (steps 1 and 2 above).  Every group boundary (w, e0, b0) is a multiple of 8, so the
-// whole walk is one run of 8-sample groups with the next group always loaded before the current one is evaluated.
-template <bool VEC> SDR_HD void dc_chunk(const DcArgs &A, long long c) {
-    const long long b0 = c * A.ch;
-    const long long b1 = (b0 + A.ch < A.n) ? b0 + A.ch : A.n;
-    const long long full_end = b0 + ((b1 - b0) & ~7LL);   // end of the whole 8-sample groups (b1 except in the last chunk)
-    const float s0 = A.state_in ? A.state_in[0] : A.last_sample;
-    const float o0 = A.state_in ? A.state_in[1] : A.last_output;
+// accessors over plain memory, bounds-checked against the end of the stream
+struct DcMemReader {
+    const float *in; long long pos, n;
+    SDR_HD float  at(long long i) const { return i < n ? in[i] : 0.0f; }
+    SDR_HD float4 get4(int q) const {
+        const long long i = pos + 4 * q;
+        return make_float4(at(i), at(i + 1), at(i + 2), at(i + 3));
+    }
+};
+struct DcMemWriter {
+    float *out; long long pos, end;
+    SDR_HD void put4(int q, const float4 &v) {
+        const long long i = pos + 4 * q;
+        if (i < end) out[i] = v.x;
+        if (i + 1 < end) out[i + 1] = v.y;
+        if (i + 2 < end) out[i + 2] = v.z;
+        if (i + 3 < end) out[i + 3] = v.w;
+    }
+};
 
-    long long e0 = b0 - A.k2; if (e0 < 0) e0 = 0;          // exact warm-up  [e0, b0)
-    long long w  = e0 - A.k1; if (w < 0) w = 0;            // cheap warm-up  [w, e0)
-    if (c == 0) { e0 = 0; w = 0; }
-    float  l = (w == 0) ? s0 : A.in[w - 1];
-    double a = (w == 0) ? (double)o0 : 0.0;
-
-    // the next two groups are always in flight before the current one is evaluated (a group is ~500 cycles of
-    // dependent arithmetic, a DRAM access under load rather more)
-    long long pos = w;
-    DcGroup   cur = DcGroup(), nx1 = DcGroup(), nx2;
-    if (pos < full_end) cur = dc_load8<VEC>(A.in, pos);
-    if (pos + 8 < full_end) nx1 = dc_load8<VEC>(A.in, pos + 8);
-    double ld = dc_widen(l);
-    for (; pos < e0; pos += 8) {
-        nx2 = nx1;
-        if (pos + 16 < full_end) nx2 = dc_load8<VEC>(A.in, pos + 16);
-#pragma unroll
-        for (int i = 0; i < 8; i++) { const double xd = dc_widen(cur.v[i]); a = dc_cheap(xd, ld, a); ld = xd; }
-        l = cur.v[7];
-        cur = nx1; nx1 = nx2;
+// The whole walk of chunk c straight out of / into global memory: the kernel for buffers that are not 16-byte aligned,
+// and what the CPU tests run (tests/emul/dc_emul.cpp).  The aligned kernel (k_dc_spec_tiles) makes the same calls with
+// rows staged through shared memory by coalesced asynchronous copies.
+SDR_HD void dc_chunk(const DcArgs &A, long long c) {
+    DcLane L;
+    dc_lane_init(A, c, L);
+    const long long tiles = dc_lane_tiles(A);
+    for (long long t = 0; t < tiles; t++) {
+        const DcMemReader rd = {A.in, L.pos, A.n};
+        DcMemWriter       wr = {A.out, L.pos, L.b1};
+        dc_lane_tile(A, c, L, rd, wr);
     }
-    float o = (float)a;   // exact when nothing was warmed up cheaply (a == o0); (float) is round-to-nearest on both sides
-    for (; pos < b0; pos += 8) {
-        nx2 = nx1;
-        if (pos + 16 < full_end) nx2 = dc_load8<VEC>(A.in, pos + 16);
-#pragma unroll
-        for (int i = 0; i < 8; i++) { o = dc_exact(cur.v[i], l, o); l = cur.v[i]; }
-        cur = nx1; nx1 = nx2;
-    }
-    if (c > 0) A.spec[c] = dc_bits(o);
-    for (; pos < full_end; pos += 8) {
-        nx2 = nx1;
-        if (pos + 16 < full_end) nx2 = dc_load8<VEC>(A.in, pos + 16);
-        DcGroup y;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { o = dc_exact(cur.v[i], l, o); l = cur.v[i]; y.v[i] = o; }
-        dc_store8<VEC>(A.out, pos, y);
-        cur = nx1; nx1 = nx2;
-    }
-#pragma unroll 1
-    for (; pos < b1; pos++) {   // ragged end of the stream (last chunk only)
-        const float x = A.in[pos];
-        o = dc_exact(x, l, o); l = x;
-        A.out[pos] = o;
-    }
-    A.fin[c] = dc_bits(o);
 }
 
 // chunk c missed iff the value it reached just before its first sample differs from the true one

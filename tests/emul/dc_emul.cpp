@@ -10,7 +10,7 @@ using namespace sdr;
 
 extern "C" int emul_dc_blocker(const float *in, float *out, long long n, float last_sample, float last_output, int ch,
                                int k1, int k2, int vec, int reverse_chunks, float *final2, unsigned long long *stats) {
-    if (n <= 0 || ch < 8 || (ch & 7) || (k1 & 7) || (k2 & 7)) return 1;
+    if (n <= 0 || ch < 32 || (ch & 31) || (k1 & 31) || (k2 & 31)) return 1;
     DcArgs A;
     A.in = in; A.out = out; A.n = n;
     A.last_sample = last_sample; A.last_output = last_output; A.state_in = nullptr;
@@ -22,7 +22,8 @@ extern "C" int emul_dc_blocker(const float *in, float *out, long long n, float l
     // the lanes of the kernel run in no particular order
     for (long long i = 0; i < A.chunks; i++) {
         const long long c = reverse_chunks ? A.chunks - 1 - i : i;
-        if (vec) dc_chunk<true>(A, c); else dc_chunk<false>(A, c);
+        (void)vec;
+        dc_chunk(A, c);
     }
     bool any = false;
     for (long long c = 1; c < A.chunks; c++)

@@ -311,7 +311,7 @@ def test_dc_blocker_parallel_repairs(ctx, ref):
     x = (3.0 * rnd(400_000, False, 22) + 1.0).astype(np.float32)
     want, ws, wo = ref.dc_blocker(x, 0.0, 7.0)
     try:
-        for chunk, k1, k2, lo in ((4096, 0, 8, 80), (512, 0, 0, 700), (2048, 6144, 512, 1)):
+        for chunk, k1, k2, lo in ((4096, 0, 32, 80), (512, 0, 0, 700), (2048, 6144, 512, 1)):
             ctx.dc_tuning(chunk, k1, k2, 0)
             st0, _ = ctx.dc_stats()
             got, fin = _dc_dev(ctx, x, 0.0, 7.0)
