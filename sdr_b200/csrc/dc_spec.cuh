@@ -125,7 +125,7 @@ struct DcLane {
 SDR_HD void dc_lane_init(const DcArgs &A, long long c, DcLane &L) {
     L.b0 = c * A.ch;
     L.b1 = (L.b0 + A.ch < A.n) ? L.b0 + A.ch : A.n;
-    if (c >= A.chunks) L.b1 = L.b0;   // no such chunk: never active
+    if (c >= A.chunks) L.b1 = 0;      // no such chunk (tail of the last warp): every tile is skipped, warm-up included
     L.pos = L.b0 - A.k1 - A.k2;
     L.l = 0.0f; L.o = 0.0f; L.a = 0.0; L.ld = 0.0;
     L.started = false;

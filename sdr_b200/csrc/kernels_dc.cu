@@ -161,16 +161,16 @@ static int env_int(const char *name, int dflt) {
 }
 
 // Tuning (dc_spec.cuh): chunk length 0 = automatic, warm-up lengths.  Every lane pays K1 + K2 warm-up samples per chunk, so
-// long chunks waste less arithmetic and re-read less input, while short ones give more lanes to hide the ~70-cycle
-// dependent step; measured on 2^28 samples: 1024 -> 77, 2048 -> 145, 4096 -> 190, 8192 -> 221 Gsamples/s (first
-// version).  Automatic = about 192 lanes per SM, between 2048 and 8192 samples.
-// The environment variables exist for measurement sweeps and for tests that force speculation to miss.
+// long chunks waste less arithmetic and re-read less input, while short ones give more lanes to hide the ~110-cycle
+// dependent step.  Measured (tools/dc_sweep.py, B200): 2^28 samples: 2048 -> 106, 4096 -> 157, 6144 -> 202, 8192 -> 214,
+// 12288 -> 165, 16384 -> 156 Gsamples/s; 2^27: 2048 -> 100, 4096 -> 153, 8192 -> 127, 16384 -> 79: the optimum sits at
+// about 32768 lanes = 7 warps per SM.  Automatic = that many lanes, between 2048 and 8192 samples.
 static void dc_tuning(const Ctx *c, long long n, int *ch, int *k1, int *k2) {
     int want = c->dc_chunk > 0 ? c->dc_chunk : env_int("SDR_B200_DC_CHUNK", 0);
     *k1 = c->dc_k1 >= 0 ? c->dc_k1 : env_int("SDR_B200_DC_K1", 6144);
     *k2 = c->dc_k2 >= 0 ? c->dc_k2 : env_int("SDR_B200_DC_K2", 4096);
     if (want <= 0) {
-        long long lanes = (long long)c->sm_count * 192;
+        long long lanes = (long long)c->sm_count * 224;
         long long per = (n + lanes - 1) / lanes;
         if (per < 2048) per = 2048;
         if (per > 8192) per = 8192;
