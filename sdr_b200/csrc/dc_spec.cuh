@@ -65,10 +65,13 @@ SDR_HD float dc_float(uint32_t u) {
 }
 
 // Exact float -> double widening with integer operations (normal numbers and zeros; denormals, infinities and NaN take
-// the conversion instruction).  On the device the float<->double conversions run on the XU pipe at about one warp
-// instruction per 23 cycles and were the bound of the first version of the speculative kernel (ncu: XU 101 % busy, three
-// conversions per step); the recurrence itself needs only the one rounding double -> float.  Checked against (double)f
-// for all 2^32 bit patterns (tests/test_dc_speculation.py::test_widen_exhaustive_sample).
+// the conversion instruction).  The float<->double conversions run on the XU pipe (about one warp instruction per 23
+// cycles per scheduler) and looked like the bound of the first, per-lane version of the kernel (three per step).  Measured
+// with the coalesced kernel the conversions win all the same: the ~8 integer instructions of a widening lengthen the
+// dependent chain more than the conversion does (2^28 samples: 215 Gsamples/s widening both operands, 237 widening the
+// difference only, 302 with conversions), so the default arithmetic flavour is DC_NATIVE and this function serves the
+// other flavours, kept selectable for measurement (SDR_B200_DC_MODE).  == (double)f for all 2^32 bit patterns
+// (tests/test_dc_speculation.py::test_widen_exhaustive_sample).
 SDR_HD double dc_widen(float f) {
     const uint32_t b = dc_bits(f);
     const uint32_t mag = b & 0x7fffffffu;
@@ -85,14 +88,24 @@ SDR_HD double dc_widen(float f) {
 }
 
 // one exact step: returns y[n] from x[n], x[n-1], y[n-1] (filter.c:155: float difference, double product and sum,
-// one rounding to float on the assignment)
-SDR_HD float dc_exact(float x, float last_sample, float last_output) {
+// one rounding to float on the assignment).  The float -> double widenings are exact whichever way they are done, so
+// the flavours below give identical bits and differ only in which pipe they load:
+//   DC_WIDEN_BOTH    integer widening of the difference and of y[n-1]: one XU conversion per step (the rounding)
+//   DC_WIDEN_DIFF    integer widening of the difference only (it is off the dependent chain); y[n-1] by conversion
+//   DC_NATIVE        both by conversion instructions: fewest instructions and the shortest dependent chain -- the
+//                    serial kernel and the repair walk, where one lane runs alone, use it
+//   DC_NATIVE_ALL    like DC_NATIVE, and the cheap warm-up converts too instead of widening
+enum { DC_WIDEN_BOTH = 0, DC_WIDEN_DIFF = 1, DC_NATIVE = 2, DC_NATIVE_ALL = 3 };
+template <int MODE> SDR_HD float dc_exact(float x, float last_sample, float last_output) {
 #if defined(__CUDA_ARCH__)
-    return __double2float_rn(__dadd_rn(dc_widen(__fsub_rn(x, last_sample)), __dmul_rn(0.997, dc_widen(last_output))));
+    const float  d = __fsub_rn(x, last_sample);
+    const double dd = (MODE >= DC_NATIVE) ? (double)d : dc_widen(d);
+    const double yd = (MODE == DC_WIDEN_BOTH) ? dc_widen(last_output) : (double)last_output;
+    return __double2float_rn(__dadd_rn(dd, __dmul_rn(0.997, yd)));
 #else
     volatile float  d = x - last_sample;                 // volatile: no contraction, no excess precision
-    volatile double p = 0.997 * dc_widen(last_output);
-    volatile double s = dc_widen(d) + p;
+    volatile double p = 0.997 * ((MODE == DC_WIDEN_BOTH) ? dc_widen(last_output) : (double)last_output);
+    volatile double s = ((MODE >= DC_NATIVE) ? (double)d : dc_widen(d)) + p;
     return (float)s;
 #endif
 }
@@ -136,7 +149,7 @@ SDR_HD long long dc_lane_tiles(const DcArgs &A) { return (A.k1 + A.k2 + A.ch) / 
 // same positions (owned tiles only; positions past the end of the stream carry the last value and are masked by the
 // writer).  Returns true when the tile produced outputs.  The accessors keep only four samples live at a time: on the
 // device they are shared-memory rows, on the host (and in the unaligned kernel) plain memory.
-template <typename Rd, typename Wr>
+template <int MODE, typename Rd, typename Wr>
 SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, Wr &wr) {
     const long long pos = L.pos;
     L.pos += SDR_DC_TILE;
@@ -161,10 +174,10 @@ SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, 
         for (int q = 0; q < SDR_DC_TILE / 4; q++) {
             const float4 v = rd.get4(q);
             double xd;
-            xd = dc_widen(v.x); a = dc_cheap(xd, ld, a); ld = xd;
-            xd = dc_widen(v.y); a = dc_cheap(xd, ld, a); ld = xd;
-            xd = dc_widen(v.z); a = dc_cheap(xd, ld, a); ld = xd;
-            xd = dc_widen(v.w); a = dc_cheap(xd, ld, a); ld = xd;
+            xd = (MODE == DC_NATIVE_ALL) ? (double)v.x : dc_widen(v.x); a = dc_cheap(xd, ld, a); ld = xd;
+            xd = (MODE == DC_NATIVE_ALL) ? (double)v.y : dc_widen(v.y); a = dc_cheap(xd, ld, a); ld = xd;
+            xd = (MODE == DC_NATIVE_ALL) ? (double)v.z : dc_widen(v.z); a = dc_cheap(xd, ld, a); ld = xd;
+            xd = (MODE == DC_NATIVE_ALL) ? (double)v.w : dc_widen(v.w); a = dc_cheap(xd, ld, a); ld = xd;
             last = v.w;
         }
         L.a = a; L.ld = ld; L.l = last;
@@ -176,7 +189,7 @@ SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, 
 #pragma unroll
         for (int q = 0; q < SDR_DC_TILE / 4; q++) {
             const float4 v = rd.get4(q);
-            o = dc_exact(v.x, l, o); o = dc_exact(v.y, v.x, o); o = dc_exact(v.z, v.y, o); o = dc_exact(v.w, v.z, o);
+            o = dc_exact<MODE>(v.x, l, o); o = dc_exact<MODE>(v.y, v.x, o); o = dc_exact<MODE>(v.z, v.y, o); o = dc_exact<MODE>(v.w, v.z, o);
             l = v.w;
         }
         L.l = l; L.o = o;
@@ -187,10 +200,10 @@ SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, 
     for (int q = 0; q < SDR_DC_TILE / 4; q++) {
         const float4 v = rd.get4(q);
         float4       y;
-        if (4 * q + 0 < m) { o = dc_exact(v.x, l, o); l = v.x; } y.x = o;
-        if (4 * q + 1 < m) { o = dc_exact(v.y, l, o); l = v.y; } y.y = o;
-        if (4 * q + 2 < m) { o = dc_exact(v.z, l, o); l = v.z; } y.z = o;
-        if (4 * q + 3 < m) { o = dc_exact(v.w, l, o); l = v.w; } y.w = o;
+        if (4 * q + 0 < m) { o = dc_exact<MODE>(v.x, l, o); l = v.x; } y.x = o;
+        if (4 * q + 1 < m) { o = dc_exact<MODE>(v.y, l, o); l = v.y; } y.y = o;
+        if (4 * q + 2 < m) { o = dc_exact<MODE>(v.z, l, o); l = v.z; } y.z = o;
+        if (4 * q + 3 < m) { o = dc_exact<MODE>(v.w, l, o); l = v.w; } y.w = o;
         wr.put4(q, y);
     }
     L.l = l; L.o = o;
@@ -221,14 +234,14 @@ struct DcMemWriter {
 // The whole walk of chunk c straight out of / into global memory: the kernel for buffers that are not 16-byte aligned,
 // and what the CPU tests run (tests/emul/dc_emul.cpp).  The aligned kernel (k_dc_spec_tiles) makes the same calls with
 // rows staged through shared memory by coalesced asynchronous copies.
-SDR_HD void dc_chunk(const DcArgs &A, long long c) {
+template <int MODE> SDR_HD void dc_chunk(const DcArgs &A, long long c) {
     DcLane L;
     dc_lane_init(A, c, L);
     const long long tiles = dc_lane_tiles(A);
     for (long long t = 0; t < tiles; t++) {
         const DcMemReader rd = {A.in, L.pos, A.n};
         DcMemWriter       wr = {A.out, L.pos, L.b1};
-        dc_lane_tile(A, c, L, rd, wr);
+        dc_lane_tile<MODE>(A, c, L, rd, wr);
     }
 }
 
@@ -243,7 +256,7 @@ SDR_HD uint32_t dc_repair_chunk(const DcArgs &A, long long c, uint32_t true_prev
     float l = A.in[b0 - 1], o = dc_float(true_prev);
     for (long long i = b0; i < b1; i++) {
         const float x = A.in[i];
-        o = dc_exact(x, l, o); l = x;
+        o = dc_exact<DC_NATIVE>(x, l, o); l = x;
         if (dc_bits(o) == dc_bits(A.out[i])) { *samples += (unsigned long long)(i - b0); return A.fin[c]; }   // merged: the rest stands
         A.out[i] = o;
     }

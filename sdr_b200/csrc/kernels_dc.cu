@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last
         if (threadIdx.x == 0) {
             for (int i = 0; i < m; i++) {
                 float x = buf[i];
-                last_output = dc_exact(x, last_sample, last_output);
+                last_output = dc_exact<DC_NATIVE>(x, last_sample, last_output);
                 last_sample = x;
                 buf[i] = last_output;
             }
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last
 // Speculative pass, buffers with any 4-byte alignment: one lane per chunk, straight out of global memory.
 __global__ void __launch_bounds__(128) k_dc_spec(DcArgs A) {
     const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (c < A.chunks) dc_chunk(A, c);
+    if (c < A.chunks) dc_chunk<DC_NATIVE>(A, c);
 }
 
 // Speculative pass, 16-byte aligned buffers.  A warp owns 32 consecutive chunks, one per lane, and all its lanes sit at
@@ -73,7 +73,7 @@ struct DcSmemWriter {
 };
 }  // namespace
 
-__global__ void __launch_bounds__(32 * DC_WARPS, 6) k_dc_spec_tiles(DcArgs A) {
+template <int MODE> __global__ void __launch_bounds__(32 * DC_WARPS, 6) k_dc_spec_tiles(DcArgs A) {
     __shared__ __align__(16) float s_in[DC_WARPS][DC_NBUF][DC_TILE_FLOATS];
     __shared__ __align__(16) float s_out[DC_WARPS][DC_TILE_FLOATS];
     const int       lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(32 * DC_WARPS, 6) k_dc_spec_tiles(DcArgs A) {
         __syncwarp();
         const DcSmemReader rd = {reinterpret_cast<const float4 *>(s_in[warp][t % DC_NBUF] + lane * DC_ROW)};
         DcSmemWriter       wr = {reinterpret_cast<float4 *>(s_out[warp] + lane * DC_ROW)};
-        dc_lane_tile(A, c, L, rd, wr);
+        dc_lane_tile<MODE>(A, c, L, rd, wr);
         // owned tiles: every lane of the warp is in its owned range at the same time (the phase depends on the offset only)
         if (rel0 + t * SDR_DC_TILE >= 0) {
             __syncwarp();
@@ -217,7 +217,12 @@ static int dc_run(Ctx *c, float last_sample, float last_output, const float *d_s
     A.fail_bits = A.fin + A.chunks;
     A.final2 = d_final2;
     const bool vec = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
-    if (vec) k_dc_spec_tiles<<<(int)((A.chunks + 32 * DC_WARPS - 1) / (32 * DC_WARPS)), 32 * DC_WARPS, 0, c->s()>>>(A);
+    const int grid_t = (int)((A.chunks + 32 * DC_WARPS - 1) / (32 * DC_WARPS));
+    static const int mode = env_int("SDR_B200_DC_MODE", DC_NATIVE);   // measurement knob: the flavours give identical bits
+    if (vec && mode == DC_WIDEN_BOTH)       k_dc_spec_tiles<DC_WIDEN_BOTH><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
+    else if (vec && mode == DC_WIDEN_DIFF)  k_dc_spec_tiles<DC_WIDEN_DIFF><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
+    else if (vec && mode == DC_NATIVE_ALL)  k_dc_spec_tiles<DC_NATIVE_ALL><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
+    else if (vec)                           k_dc_spec_tiles<DC_NATIVE><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
     else     k_dc_spec<<<(int)((A.chunks + 127) / 128), 128, 0, c->s()>>>(A);
     SDR_LAUNCH_CHECK(c);
     k_dc_repair<<<1, 1024, 0, c->s()>>>(A);

@@ -22,8 +22,9 @@ extern "C" int emul_dc_blocker(const float *in, float *out, long long n, float l
     // the lanes of the kernel run in no particular order
     for (long long i = 0; i < A.chunks; i++) {
         const long long c = reverse_chunks ? A.chunks - 1 - i : i;
-        (void)vec;
-        dc_chunk(A, c);
+        // `vec` selects the arithmetic flavour here (0 widen both, 1 widen the difference, 2 native, 3 native incl. the cheap warm-up): identical bits
+        if (vec == 0) dc_chunk<DC_WIDEN_BOTH>(A, c); else if (vec == 1) dc_chunk<DC_WIDEN_DIFF>(A, c);
+        else if (vec == 2) dc_chunk<DC_NATIVE>(A, c); else dc_chunk<DC_NATIVE_ALL>(A, c);
     }
     bool any = false;
     for (long long c = 1; c < A.chunks; c++)

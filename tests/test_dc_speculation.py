@@ -42,7 +42,7 @@ def aligned(n, offset_floats=0):
     return raw[skew + offset_floats: skew + offset_floats + n]
 
 
-def run(lib, x, s0=0.0, o0=0.0, ch=2048, k1=6144, k2=4096, vec=1, reverse=0, offset=0):
+def run(lib, x, s0=0.0, o0=0.0, ch=2048, k1=6144, k2=4096, vec=2, reverse=0, offset=0):
     xin = aligned(len(x), offset)
     xin[:] = x
     out = aligned(len(x), offset)
@@ -94,6 +94,8 @@ def test_scalar_access_path_and_lane_order(emul, port):
     check(emul, port, x, ch=1024, k1=512, k2=2048, vec=0, offset=1)
     check(emul, port, x, ch=1024, k1=512, k2=2048, vec=0, offset=3, reverse=1)
     check(emul, port, x, ch=1024, k1=512, k2=2048, vec=1, reverse=1)
+    check(emul, port, x, ch=1024, k1=512, k2=2048, vec=3)
+    check(emul, port, x, ch=1024, k1=512, k2=2048, vec=2)     # `vec` = arithmetic flavour of the exact step (identical bits)
 
 
 def test_short_warmup_is_repaired(emul, port):

@@ -18,7 +18,8 @@ def main():
         n = 1 << log2n
         x, y, fin = ctx.alloc(4 * n), ctx.alloc(4 * n), ctx.alloc(8)
         ctx.synth_noise(x, n)
-        for chunk, k1, k2 in ((0, -1, -1), (2048, -1, -1), (3072, -1, -1), (4096, -1, -1), (6144, -1, -1), (8192, -1, -1),
+        settings = ((0, -1, -1), (4096, -1, -1), (8192, -1, -1)) if os.environ.get("DC_SWEEP_SHORT") else None
+        for chunk, k1, k2 in settings or ((0, -1, -1), (2048, -1, -1), (3072, -1, -1), (4096, -1, -1), (6144, -1, -1), (8192, -1, -1),
                               (12288, -1, -1), (16384, -1, -1), (8192, 4096, -1), (8192, 8192, -1), (8192, -1, 3072), (4096, -1, 3072)):
             ctx.dc_tuning(chunk, k1, k2, -1)
             for _ in range(2):
@@ -35,7 +36,8 @@ def main():
             gs = n / (ms * 1e-3) / 1e9
             print(json.dumps({"log2n": log2n, "chunk": chunk, "k1": k1, "k2": k2, "ms": round(ms, 4), "Gsamples_per_s": round(gs, 1),
                               "hbm_frac": round(gs * 8 / PEAK, 3), "chunks_per_call": (st1[1] - st0[1]) // 5,
-                              "repaired_per_call": (st1[2] - st0[2]) / 5, "parallel": par}), flush=True)
+                              "repaired_per_call": (st1[2] - st0[2]) / 5, "parallel": par,
+                              "mode": os.environ.get("SDR_B200_DC_MODE", "default")}), flush=True)
         ctx.dc_tuning()
         for b in (x, y, fin):
             b.free()

@@ -2,10 +2,13 @@
 # One GPU-box session; everything lands in gpurun_out/ so that a session cut short still leaves what it finished.
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --durations=10 > $O/t_all.log 2>&1; echo "all gpu tests rc=$?" | tee -a $O/summary.txt
-tail -16 $O/t_all.log
+rm -f $O/dc_modes.txt
+timeout 900 python -m pytest tests -m gpu -q --durations=5 > $O/t_all.log 2>&1; echo "all gpu tests rc=$?" | tee -a $O/summary.txt
+tail -9 $O/t_all.log
+for mode in 2 3; do
+SDR_B200_DC_MODE=$mode DC_SWEEP_SHORT=1 timeout 200 python tools/dc_sweep.py 28 27 >> $O/dc_modes.txt 2>> $O/dc_modes.err; echo "mode $mode rc=$?" | tee -a $O/summary.txt
+done
+cat $O/dc_modes.txt
+timeout 300 python tools/dc_sweep.py 28 > $O/dc_sweep.txt 2> $O/dc_sweep.err; echo "dc sweep rc=$?" | tee -a $O/summary.txt
 timeout 300 python tools/bench_configs.py 27 > $O/bench_configs.txt 2> $O/bench_configs.err; echo "bench_configs rc=$?" | tee -a $O/summary.txt
-timeout 300 python bench.py --steps 20 --warmup 3 > $O/bench.json 2> $O/bench.err; echo "bench rc=$?" | tee -a $O/summary.txt
-timeout 240 ncu --set full --clock-control none --import-source on -k regex:'k_fm_front_ring' -c 1 -s 2 -o $O/prof_fm_front -f python tools/bench_configs.py 26 > $O/ncu_fm.log 2>&1; echo "ncu fm rc=$?" | tee -a $O/summary.txt
-timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu > $O/launches_bench.log 2>&1; echo "ncu launches rc=$?" | tee -a $O/summary.txt
-python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $O/summary.txt
+timeout 240 ncu --set full --clock-control none --import-source on -k regex:'k_dc_spec' -c 1 -s 1 -o $O/prof_dc4 -f python tools/dc_probe.py 28 > $O/ncu_dc4.log 2>&1; echo "ncu rc=$?" | tee -a $O/summary.txt
