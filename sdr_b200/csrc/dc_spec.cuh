@@ -69,7 +69,8 @@ SDR_HD float dc_float(uint32_t u) {
 // cycles per scheduler) and looked like the bound of the first, per-lane version of the kernel (three per step).  Measured
 // with the coalesced kernel the conversions win all the same: the ~8 integer instructions of a widening lengthen the
 // dependent chain more than the conversion does (2^28 samples: 215 Gsamples/s widening both operands, 237 widening the
-// difference only, 302 with conversions), so the default arithmetic flavour is DC_NATIVE and this function serves the
+// difference only, 302 with conversions, 312 when the cheap warm-up converts too), so the default arithmetic flavour is
+// DC_NATIVE_ALL and this function serves the
 // other flavours, kept selectable for measurement (SDR_B200_DC_MODE).  == (double)f for all 2^32 bit patterns
 // (tests/test_dc_speculation.py::test_widen_exhaustive_sample).
 SDR_HD double dc_widen(float f) {

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last
 // Speculative pass, buffers with any 4-byte alignment: one lane per chunk, straight out of global memory.
 __global__ void __launch_bounds__(128) k_dc_spec(DcArgs A) {
     const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (c < A.chunks) dc_chunk<DC_NATIVE>(A, c);
+    if (c < A.chunks) dc_chunk<DC_NATIVE_ALL>(A, c);
 }
 
 // Speculative pass, 16-byte aligned buffers.  A warp owns 32 consecutive chunks, one per lane, and all its lanes sit at
@@ -161,10 +161,10 @@ static int env_int(const char *name, int dflt) {
 }
 
 // Tuning (dc_spec.cuh): chunk length 0 = automatic, warm-up lengths.  Every lane pays K1 + K2 warm-up samples per chunk, so
-// long chunks waste less arithmetic and re-read less input, while short ones give more lanes to hide the ~110-cycle
-// dependent step.  Measured (tools/dc_sweep.py, B200): 2^28 samples: 2048 -> 106, 4096 -> 157, 6144 -> 202, 8192 -> 214,
-// 12288 -> 165, 16384 -> 156 Gsamples/s; 2^27: 2048 -> 100, 4096 -> 153, 8192 -> 127, 16384 -> 79: the optimum sits at
-// about 32768 lanes = 7 warps per SM.  Automatic = that many lanes, between 2048 and 8192 samples.
+// long chunks waste less arithmetic and re-read less input, while short ones give more lanes to hide the ~70-cycle
+// dependent step.  Measured (tools/dc_sweep.py, profiles/r01b_dc_sweep.txt, B200), 2^28 samples: 2048 -> 127, 4096 -> 208,
+// 6144 -> 272, 8192 -> 303, 12288 -> 239, 16384 -> 224 Gsamples/s; 2^27: 4096 -> 208, 8192 -> 178: the optimum sits at about
+// 32768 lanes = 7 warps per SM.  Automatic = that many lanes, between 2048 and 8192 samples.
 static void dc_tuning(const Ctx *c, long long n, int *ch, int *k1, int *k2) {
     int want = c->dc_chunk > 0 ? c->dc_chunk : env_int("SDR_B200_DC_CHUNK", 0);
     *k1 = c->dc_k1 >= 0 ? c->dc_k1 : env_int("SDR_B200_DC_K1", 6144);
@@ -218,11 +218,11 @@ static int dc_run(Ctx *c, float last_sample, float last_output, const float *d_s
     A.final2 = d_final2;
     const bool vec = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
     const int grid_t = (int)((A.chunks + 32 * DC_WARPS - 1) / (32 * DC_WARPS));
-    static const int mode = env_int("SDR_B200_DC_MODE", DC_NATIVE);   // measurement knob: the flavours give identical bits
+    static const int mode = env_int("SDR_B200_DC_MODE", DC_NATIVE_ALL);   // measurement knob: the flavours give identical bits
     if (vec && mode == DC_WIDEN_BOTH)       k_dc_spec_tiles<DC_WIDEN_BOTH><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
     else if (vec && mode == DC_WIDEN_DIFF)  k_dc_spec_tiles<DC_WIDEN_DIFF><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
-    else if (vec && mode == DC_NATIVE_ALL)  k_dc_spec_tiles<DC_NATIVE_ALL><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
-    else if (vec)                           k_dc_spec_tiles<DC_NATIVE><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
+    else if (vec && mode == DC_NATIVE)      k_dc_spec_tiles<DC_NATIVE><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
+    else if (vec)                           k_dc_spec_tiles<DC_NATIVE_ALL><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
     else     k_dc_spec<<<(int)((A.chunks + 127) / 128), 128, 0, c->s()>>>(A);
     SDR_LAUNCH_CHECK(c);
     k_dc_repair<<<1, 1024, 0, c->s()>>>(A);
