@@ -4,7 +4,7 @@ Python here is only the host-side mirror of the reference's Haskell interface (r
 the C ABI in ``include/sdr_b200.h``; all compute is in ``sdr_b200/lib/libsdr_b200.so`` (hand-written CUDA).
 """
 from ._lib import (SDR_ARITH_EXACT, SDR_ARITH_FAST, SDR_DEVICE, SDR_HOST, SDR_HOST_PINNED, SdrError, LIB_PATH)  # noqa: F401
-from .device import Context, DeviceBuffer, Event, PinnedArray, device_count, has_cuda  # noqa: F401
+from .device import Context, DeviceBuffer, Event, PinnedArray, device_count, featureSelect, hasCUDA, has_cuda  # noqa: F401
 from .filter import (Decimator, Filter, NativePipe, Resampler, cudaDecimatorC, cudaDecimatorR, cudaDecimatorSymR,  # noqa: F401
                      cudaFilterC, cudaFilterR, cudaFilterSymR, cudaResamplerC, cudaResamplerR, default_context,
                      firDecimator, firFilter, firResampler, pipeFirDecimator, pipeFirFilter, pipeFirResampler)

@@ -154,6 +154,22 @@ def has_cuda():
     return bool(L.lib.sdr_has_cuda())
 
 
+def featureSelect(info, default, options):
+    """``featureSelect :: CPUInfo -> a -> [(CPUInfo -> Bool, a)] -> a`` (hs_sources/SDR/CPUID.hs:100-104): the first
+    implementation whose predicate accepts `info`, else `default`.  `info` is whatever the predicates test -- for this
+    backend ``hasCUDA`` below ignores it and asks the library; a caller mixing it with its own predicates passes its own
+    info object through unchanged, exactly as the reference threads its CPUInfo."""
+    for pred, impl in options:
+        if pred(info):
+            return impl
+    return default
+
+
+def hasCUDA(_info=None):
+    """the predicate that goes in front of hasAVX / hasSSE42 in a featureSelect list (CPUID.hs:87-104)"""
+    return has_cuda()
+
+
 def device_count():
     n = C.c_int()
     L.check(L.lib.sdr_device_count(C.byref(n)))

@@ -39,6 +39,19 @@ def test_no_cpu_fallback_without_device():
         sdr_b200.scaleFast(2.0, np.zeros(16, np.float32))
 
 
+def test_feature_select_is_first_match_with_default():
+    """featureSelect (CPUID.hs:100-104): first matching (predicate, implementation) pair, else the default; hasCUDA is
+    the predicate this backend adds in front of the reference's hasAVX / hasSSE42"""
+    import sdr_b200
+    info = {"avx": True, "sse42": True}
+    opts = [(lambda i: False, "cuda"), (lambda i: i["avx"], "avx"), (lambda i: i["sse42"], "sse")]
+    assert sdr_b200.featureSelect(info, "c", opts) == "avx"
+    assert sdr_b200.featureSelect({"avx": False, "sse42": False}, "c", opts) == "c"
+    assert sdr_b200.featureSelect(info, "c", []) == "c"
+    want = "cuda" if sdr_b200.has_cuda() else "avx"
+    assert sdr_b200.featureSelect(info, "c", [(sdr_b200.hasCUDA, "cuda")] + opts[1:]) == want
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "sdr_b200")
     for dirpath, _, files in os.walk(pkg):
