@@ -81,6 +81,11 @@ int sdr_ctx_create(int device, sdr_ctx_t **ctx);
 int sdr_ctx_destroy(sdr_ctx_t *ctx);
 int sdr_ctx_sync(sdr_ctx_t *ctx);                       /* wait for everything enqueued on the ctx stream */
 int sdr_ctx_set_arith(sdr_ctx_t *ctx, int arith_mode);  /* SDR_ARITH_* for handles created afterwards */
+/* Real stride-1 filters of 32 / 64 / 128 taps (fastFilterR / fastFilterSymR, Filter.hs:193-261): evaluate the tuned
+ * kernel with 2-parallel fast-FIR arithmetic (3 half-length sub-filters per 2 outputs, 17 % fewer FP32 operations;
+ * sdr_b200/csrc/fir_ffa.cuh).  Agrees with the direct form to rounding (1.5e-6 of the output scale, bar 1e-5), not
+ * bit for bit; off by default (environment default: SDR_B200_FIR_FFA=1). */
+int sdr_ctx_set_fast_fir(sdr_ctx_t *ctx, int on);
 /* `hasCUDA` predicate for featureSelect (CPUID.hs:100-104): 1 when a sm_100 device is usable, else 0 */
 int sdr_has_cuda(void);
 int sdr_ctx_sm_count(sdr_ctx_t *ctx, int *sms);

@@ -82,6 +82,7 @@ _sig("sdr_ctx_create", _I, c_void_pp)
 _sig("sdr_ctx_destroy", _P)
 _sig("sdr_ctx_sync", _P)
 _sig("sdr_ctx_set_arith", _P, _I)
+_sig("sdr_ctx_set_fast_fir", _P, _I)
 _sig("sdr_ctx_sm_count", _P, C.POINTER(_I))
 _sig("sdr_dev_alloc", _P, _SZ, c_void_pp)
 _sig("sdr_dev_free", _P, _P)

@@ -35,6 +35,7 @@ struct Ctx {
     int          reserve_sms = 0;        // SMs the persistent kernels leave free (for a concurrent NCCL kernel)
     int          sm_count    = 0;
     int          arith       = SDR_ARITH_FAST;
+    bool         fir_ffa     = false;    // real stride-1 filters: 2-parallel fast-FIR arithmetic (kernels_real.cu)
     long long    launches    = 0;
     // pinned + device staging for HOST-pointer calls (grown on demand)
     void  *h_stage = nullptr; size_t h_stage_bytes = 0;

@@ -116,6 +116,7 @@ int sdr_ctx_create(int device, sdr_ctx_t **ctx) {
     Ctx *c = new Ctx();
     c->device = device;
     c->sm_count = p.multiProcessorCount;
+    if (const char *e = getenv("SDR_B200_FIR_FFA")) c->fir_ffa = atoi(e) != 0;
     SDR_CUDA(cudaSetDevice(device));
     SDR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     SDR_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
@@ -141,6 +142,13 @@ int sdr_ctx_destroy(sdr_ctx_t *ctx) {
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->side);
     delete c;
+    return SDR_OK;
+}
+
+int sdr_ctx_set_fast_fir(sdr_ctx_t *ctx, int on) {
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return set_error(SDR_EINVAL, "sdr_ctx_set_fast_fir: null ctx");
+    c->fir_ffa = on != 0;
     return SDR_OK;
 }
 

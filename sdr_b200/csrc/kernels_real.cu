@@ -12,7 +12,10 @@
 //
 // Rooflines: the 64-tap filter needs 64 FMA per 8 algorithmic bytes -- it is FP32-pipe bound
 // (about 0.64 of the HBM roofline at the measured FMA peak); the 3/10 resampler needs 9 FMA per 5.2 bytes -- HBM bound.
+#include "fir_ffa.cuh"
 #include "ring_common.cuh"
+
+#include <cstdlib>
 
 namespace sdr {
 
@@ -90,10 +93,62 @@ k_fir_r_ring(const float *__restrict__ in, float *__restrict__ out, const float 
     }
 }
 
+// Same ring, 2-parallel fast-FIR arithmetic (fir_ffa.cuh): three half-length sub-filters per two outputs instead of
+// four -- 17 % fewer FP32-pipe operations per lane pass for a kernel that pipe bounds.  Results agree with the direct
+// form to rounding (1.5e-6 of the output scale), not bit for bit, so it is opt-in (sdr_ctx_set_fast_fir, SDR_B200_FIR_FFA=1) until the
+// full-size parity properties that rely on ring == generic have a tolerance-based twin.
 template <int T, int R, int S>
+__global__ void __launch_bounds__(256, 1)
+k_fir_r_ffa_ring(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ taps, long long n_slots) {
+    typedef FirRCfg<T, R, S> C;
+    const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long q = n_slots / gridDim.x, rem = n_slots % gridDim.x;
+    long long s0 = blockIdx.x * q + (blockIdx.x < rem ? blockIdx.x : rem);
+    int cnt = (int)(q + (blockIdx.x < rem ? 1 : 0));
+    if (cnt == 0) return;
+
+    typename C::Ring ring;
+    ring.init(smem, reinterpret_cast<const unsigned char *>(in + s0 * C::SLOT_OUT), cnt);
+    ring.prologue(warp, lane, 8);
+
+    float h0[T / 2], h1[T / 2], hs[T / 2];
+#pragma unroll
+    for (int j = 0; j < T / 2; j++) {
+        h0[j] = __ldg(taps + 2 * j);
+        h1[j] = __ldg(taps + 2 * j + 1);
+        hs[j] = __fadd_rn(h0[j], h1[j]);
+    }
+
+    for (int u = warp; u < cnt; u += 8) {
+        ring.wait_slot(u);
+        const float *slot_base = reinterpret_cast<const float *>(smem + (u % C::NS) * C::SLOT_BYTES);
+        float *out_slot = out + (s0 + u) * C::SLOT_OUT;
+#pragma unroll 1
+        for (int p = 0; p < S; p++) {
+            const float4 *w = reinterpret_cast<const float4 *>(slot_base + (p * 32 + lane) * R);
+            float acc[R];
+            fir_ffa_lane<T, R>(w, h0, h1, hs, acc);
+            float *os = out_slot + (p * 32 + lane) * R;
+            if (vec_store) {
+                float4 *o = reinterpret_cast<float4 *>(os);
+#pragma unroll
+                for (int r = 0; r < R; r += 4) o[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) os[r] = acc[r];
+            }
+        }
+        ring.release_and_refill(u, lane);
+    }
+}
+
+template <int T, int R, int S, bool FFA = false>
 static int launch_fir_r(Ctx *c, const float *d_taps, const float *d_in, long long n_in, float *d_out, long long num,
                         long long *done) {
     typedef FirRCfg<T, R, S> C;
+    auto kernel = FFA ? k_fir_r_ffa_ring<T, R, S> : k_fir_r_ring<T, R, S>;
     long long n_slots = num / C::SLOT_OUT;
     long long by_in = (n_in - C::HALO) / C::SLOT_OUT;
     if (by_in < n_slots) n_slots = by_in;
@@ -101,13 +156,13 @@ static int launch_fir_r(Ctx *c, const float *d_taps, const float *d_in, long lon
     SDR_TRY(c->bind());
     static thread_local int attr_dev = -1;
     if (attr_dev != c->device) {
-        SDR_CUDA(cudaFuncSetAttribute(k_fir_r_ring<T, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::Ring::SMEM_BYTES));
+        SDR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::Ring::SMEM_BYTES));
         attr_dev = c->device;
     }
     int sms = c->sm_count - c->reserve_sms;
     if (sms < 1) sms = 1;
     int grid = (int)(n_slots < sms ? n_slots : sms);
-    k_fir_r_ring<T, R, S><<<grid, 256, C::Ring::SMEM_BYTES, c->s()>>>(d_in, d_out, d_taps, n_slots);
+    kernel<<<grid, 256, C::Ring::SMEM_BYTES, c->s()>>>(d_in, d_out, d_taps, n_slots);
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     *done = n_slots * C::SLOT_OUT;
@@ -119,6 +174,10 @@ int launch_fir_r_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_
     *done = 0;
     *name = "fir_tile";
     if (D != 1 || (((uintptr_t)d_in) & 15) != 0) return SDR_OK;   // TMA needs a 16-byte aligned source; any output alignment
+    const bool ffa = c->fir_ffa;   // sdr_ctx_set_fast_fir / SDR_B200_FIR_FFA
+    if (T == 64 && ffa) { *name = "fir_r_ffa_ring<64,20,6>"; return launch_fir_r<64, 20, 6, true>(c, d_taps, d_in, n_in, d_out, num, done); }
+    if (T == 32 && ffa) { *name = "fir_r_ffa_ring<32,20,6>"; return launch_fir_r<32, 20, 6, true>(c, d_taps, d_in, n_in, d_out, num, done); }
+    if (T == 128 && ffa) { *name = "fir_r_ffa_ring<128,20,6>"; return launch_fir_r<128, 20, 6, true>(c, d_taps, d_in, n_in, d_out, num, done); }
     if (T == 64) { *name = "fir_r_ring<64,20,6>"; return launch_fir_r<64, 20, 6>(c, d_taps, d_in, n_in, d_out, num, done); }
     if (T == 32) { *name = "fir_r_ring<32,20,6>"; return launch_fir_r<32, 20, 6>(c, d_taps, d_in, n_in, d_out, num, done); }
     if (T == 128) { *name = "fir_r_ring<128,20,6>"; return launch_fir_r<128, 20, 6>(c, d_taps, d_in, n_in, d_out, num, done); }

@@ -21,6 +21,10 @@ class Context:
     def set_arith(self, mode):
         L.check(L.lib.sdr_ctx_set_arith(self.h, mode))
 
+    def set_fast_fir(self, on=True):
+        """real 32/64/128-tap stride-1 filters: 2-parallel fast-FIR arithmetic in the tuned kernel (csrc/fir_ffa.cuh)"""
+        L.check(L.lib.sdr_ctx_set_fast_fir(self.h, int(bool(on))))
+
     def sync(self):
         L.check(L.lib.sdr_ctx_sync(self.h))
 

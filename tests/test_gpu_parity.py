@@ -653,6 +653,38 @@ def test_stream_real_filter_tuned_vs_generic_and_oracle(sdr, L, ctx, ref, T, log
         b_.free()
 
 
+@pytest.mark.parametrize("T", [64, 32, 128])
+@pytest.mark.parametrize("log2n", [18, 26])
+def test_stream_real_filter_fast_fir_vs_direct_and_oracle(sdr, L, ctx, ref, T, log2n):
+    """cfg1 with the opt-in 2-parallel fast-FIR arithmetic (sdr_ctx_set_fast_fir): same ring, sums associated differently,
+    so parity is the path's tolerance against the reference AVX filter AND against the direct-form ring kernel"""
+    n = 1 << log2n
+    half = synth.windowed_sinc_taps(T, 1 / 4)[:T // 2]
+    f = sdr.cudaFilterSymR(half)
+    num = n - T + 1
+    x, y, y2 = ctx.alloc(4 * n + 64), ctx.alloc(4 * num + 64), ctx.alloc(4 * num + 64)
+    ctx.synth_noise(x, n)
+    try:
+        L.check(L.lib.sdr_filter_stream(f.handle, x.ptr, n, y2.ptr, num))
+        assert f.last_kernel().startswith("fir_r_ring"), f.last_kernel()
+        ctx.set_fast_fir(True)
+        L.check(L.lib.sdr_filter_stream(f.handle, x.ptr, n, y.ptr, num))
+        assert f.last_kernel().startswith("fir_r_ffa_ring"), f.last_kernel()
+        for m0 in sorted({0, 3839, 3840, num // 2, num - 4000}):
+            cnt = 2048
+            xs = synth.noise(cnt + T, first=m0)
+            want = ref.filter("filterAVXSymmetricRR", cnt, half, xs)
+            got = y.to_host(np.float32, cnt, offset_bytes=4 * m0)
+            close(got, want)
+            close(got, y2.to_host(np.float32, cnt, offset_bytes=4 * m0))
+        # the ragged end is finished by the generic kernel either way: the last outputs agree bit for bit
+        assert np.array_equal(y.to_host(np.float32, 8, offset_bytes=4 * (num - 8)), y2.to_host(np.float32, 8, offset_bytes=4 * (num - 8)))
+    finally:
+        ctx.set_fast_fir(False)
+        for b_ in (x, y, y2):
+            b_.free()
+
+
 @pytest.mark.parametrize("T", [90, 31])
 @pytest.mark.parametrize("log2n", [18, 26])
 def test_stream_real_resampler_tuned_vs_generic_and_oracle(sdr, L, ctx, ref, T, log2n):

@@ -51,7 +51,11 @@ def main():
     nr = 2 * n   # real samples available in the buffer
     num = nr - 64 + 1
     ms = timed(ctx, lambda: L.check(L.lib.sdr_filter_stream(f.handle, x.ptr, nr, y.ptr, num)))
-    report("cfg1 filter 64-tap sym real", ms, nr, 8.0)
+    report("cfg1 filter 64-tap sym real", ms, nr, 8.0, f.last_kernel())
+    ctx.set_fast_fir(True)
+    ms = timed(ctx, lambda: L.check(L.lib.sdr_filter_stream(f.handle, x.ptr, nr, y.ptr, num)))
+    report("cfg1 filter 64-tap sym real, 2-parallel fast-FIR arithmetic (opt-in)", ms, nr, 8.0, f.last_kernel())
+    ctx.set_fast_fir(False)
     # cfg3: fastResamplerR 3/10, 90 taps, real
     t_res = synth.windowed_sinc_taps(90, 1 / 20, gain=3.0)
     r = sdr_b200.cudaResamplerR(3, 10, t_res, ctx=ctx, sizeMultiple=8)
