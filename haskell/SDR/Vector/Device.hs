@@ -133,8 +133,13 @@ fromStorable v = do
 toStorable :: Storable a => DVector a -> IO (VS.Vector a)
 toStorable (DVector b o n) = download b o n
 
+-- | one context (device 0, one stream) for every vector of the process: created on first use
+theCtx :: Ptr Ctx
+theCtx = unsafePerformIO $ alloca $ \pp -> check (c_ctxCreate 0 pp) >> peek pp
+{-# NOINLINE theCtx #-}
+
 defaultCtx :: IO (Ptr Ctx)
-defaultCtx = alloca $ \pp -> check (c_ctxCreate 0 pp) >> peek pp
+defaultCtx = return theCtx
 
 -- | 'SDR.Filter.fastDecimatorC' (Filter.hs:352-356) over device vectors: the SAME record type, instantiated at
 --   DVector, so @firDecimator deci 8192@ is the unmodified reference pipe moving HBM-resident buffers.  Both closures
