@@ -308,6 +308,13 @@ int launch_res_r_fast(Ctx *c, int L, int M, int n_taps, const float *d_plain_tap
     *done = 0;
     *name = "fir_tile";
     if ((((uintptr_t)d_in) & 15) != 0) return SDR_OK;
+    // passes per ring slot (S): smaller slots = more, finer-grained copies in flight.  Measurement knob; every S gives
+    // the same bits (a lane's arithmetic does not depend on how lanes are grouped into slots).
+    static const int res_s = getenv("SDR_B200_RES_S") ? atoi(getenv("SDR_B200_RES_S")) : 2;
+    if (L == 3 && M == 10 && n_taps == 90 && res_s == 1) {
+        *name = "res_r_ring<3,10,90,6,1>";
+        return launch_res_r<3, 10, 90, 6, 1>(c, d_plain_taps, d_in, n_in, d_out, num, done);
+    }
     if (L == 3 && M == 10 && n_taps == 90) {
         *name = "res_r_ring<3,10,90,6,2>";
         return launch_res_r<3, 10, 90, 6, 2>(c, d_plain_taps, d_in, n_in, d_out, num, done);
