@@ -65,12 +65,28 @@ def ncu_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled from a thread every millisecond (the
+    timed region of the default run is only ~8 ms long, an `nvidia-smi -lms 100` loop would see it once or twice);
+    nvidia-smi is the fallback when the NVML binding is unusable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
+                    (0x80, "hw_power_brake_slowdown"))
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -79,11 +95,36 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.time(), sm, mask))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+            if not rows:
+                return None
+            mask = 0
+            for r in rows:
+                mask |= r[2]
+            return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(name for bit, name in self.NVML_REASONS if mask & bit), "samples": len(rows), "source": "nvml, 1 ms poll"}
         if not self.proc:
             return None
         time.sleep(0.15)
@@ -101,7 +142,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return None
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
