@@ -387,17 +387,28 @@ int launch_scale(Ctx *c, float k, const float *d_in, float *d_out, long long n) 
     return SDR_OK;
 }
 
-// 4 consecutive samples per thread: two 16-byte loads (+ one L1-resident re-read for the predecessor of the first
-// sample), four independent branch-free discriminators, one 16-byte store
+// 4 consecutive samples per thread and trip: two 16-byte loads (+ one L1-resident re-read for the predecessor of the
+// first sample), four independent discriminators, one 16-byte store.  Two trips are in flight per thread (all six loads
+// are issued before the first discriminator): with one, ncu showed the kernel waiting on memory (long_scoreboard 12.8
+// warps per issue at 75 % of DRAM bandwidth).
+__device__ __forceinline__ float4 fm_demod_group(const float4 a, const float4 b, const float2 l) {
+    const float2 s0 = make_float2(a.x, a.y), s1 = make_float2(a.z, a.w), s2 = make_float2(b.x, b.y), s3 = make_float2(b.z, b.w);
+    return make_float4(fm_phase(s0, l), fm_phase(s1, s0), fm_phase(s2, s1), fm_phase(s3, s2));
+}
 __global__ void __launch_bounds__(256) k_fm_demod4(float last_re, float last_im, const float2 *__restrict__ last_ptr,
                                                    const float4 *__restrict__ in, float4 *__restrict__ out, long long n4) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+        const long long i2 = i + stride;
+        const bool      two = i2 < n4;
         const float4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
-        const float2 s0 = make_float2(a.x, a.y), s1 = make_float2(a.z, a.w), s2 = make_float2(b.x, b.y), s3 = make_float2(b.z, b.w);
+        float4 a2 = a, b2 = b, p2 = a;
+        if (two) { a2 = __ldg(in + 2 * i2); b2 = __ldg(in + 2 * i2 + 1); p2 = __ldg(in + 2 * i2 - 1); }
         float2 l;
         if (i == 0) l = last_ptr ? *last_ptr : make_float2(last_re, last_im);
         else { const float4 p = __ldg(in + 2 * i - 1); l = make_float2(p.z, p.w); }
-        out[i] = make_float4(fm_phase(s0, l), fm_phase(s1, s0), fm_phase(s2, s1), fm_phase(s3, s2));
+        out[i] = fm_demod_group(a, b, l);
+        if (two) out[i2] = fm_demod_group(a2, b2, make_float2(p2.z, p2.w));
     }
 }
 __global__ void __launch_bounds__(256) k_fm_demod(float last_re, float last_im, const float2 *__restrict__ last_ptr,
