@@ -119,14 +119,15 @@ SDR_HD double dc_cheap(double xd, double ld, double a) {
 #endif
 }
 
-// ---- one lane's walk over its chunk, in tiles of 32 samples ----------------------------------------------------------
+// ---- one lane's walk over its chunk, in tiles of TILE samples ----------------------------------------------------------
 // A lane visits positions [b0 - K1 - K2, b1) of the stream in 32-sample tiles (chunk and warm-up lengths are multiples
-// of 32, so a tile lies in exactly one phase and every lane of a warp is in the same phase at the same time):
+// of the tile, so a tile lies in exactly one phase and every lane of a warp is in the same phase at the same time):
 //   cheap warm-up  [b0 - K1 - K2, b0 - K2)   double state, one DFMA per sample
 //   exact warm-up  [b0 - K2, b0)             the reference's arithmetic, nothing stored
 //   owned          [b0, b1)                  the reference's arithmetic, outputs stored
 // Tiles before the start of the stream are skipped; the lane then starts at position 0 from the true state.
-#define SDR_DC_TILE 32
+// TILE (32 or 64 samples) is the granularity of the walk and of the staged copies: chunk and warm-up lengths are
+// multiples of it.
 
 struct DcLane {
     long long b0, b1;    // owned range
@@ -144,16 +145,16 @@ SDR_HD void dc_lane_init(const DcArgs &A, long long c, DcLane &L) {
     L.l = 0.0f; L.o = 0.0f; L.a = 0.0; L.ld = 0.0;
     L.started = false;
 }
-SDR_HD long long dc_lane_tiles(const DcArgs &A) { return (A.k1 + A.k2 + A.ch) / SDR_DC_TILE; }
+template <int TILE> SDR_HD long long dc_lane_tiles(const DcArgs &A) { return (A.k1 + A.k2 + A.ch) / TILE; }
 
 // One tile.  `rd.get4(q)` delivers samples in[pos + 4q .. pos + 4q + 3], `wr.put4(q, v)` takes the four outputs of the
 // same positions (owned tiles only; positions past the end of the stream carry the last value and are masked by the
 // writer).  Returns true when the tile produced outputs.  The accessors keep only four samples live at a time: on the
 // device they are shared-memory rows, on the host (and in the unaligned kernel) plain memory.
-template <int MODE, typename Rd, typename Wr>
+template <int MODE, int TILE, typename Rd, typename Wr>
 SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, Wr &wr) {
     const long long pos = L.pos;
-    L.pos += SDR_DC_TILE;
+    L.pos += TILE;
     if (pos < 0 || pos >= L.b1) return false;
     if (!L.started) {
         L.started = true;
@@ -172,7 +173,7 @@ SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, 
         double a = L.a, ld = L.ld;
         float  last = L.l;
 #pragma unroll
-        for (int q = 0; q < SDR_DC_TILE / 4; q++) {
+        for (int q = 0; q < TILE / 4; q++) {
             const float4 v = rd.get4(q);
             double xd;
             xd = (MODE == DC_NATIVE_ALL) ? (double)v.x : dc_widen(v.x); a = dc_cheap(xd, ld, a); ld = xd;
@@ -188,7 +189,7 @@ SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, 
     float l = L.l, o = L.o;
     if (pos < L.b0) {
 #pragma unroll
-        for (int q = 0; q < SDR_DC_TILE / 4; q++) {
+        for (int q = 0; q < TILE / 4; q++) {
             const float4 v = rd.get4(q);
             o = dc_exact<MODE>(v.x, l, o); o = dc_exact<MODE>(v.y, v.x, o); o = dc_exact<MODE>(v.z, v.y, o); o = dc_exact<MODE>(v.w, v.z, o);
             l = v.w;
@@ -196,9 +197,9 @@ SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, 
         L.l = l; L.o = o;
         return false;
     }
-    const int m = (L.b1 - pos < SDR_DC_TILE) ? (int)(L.b1 - pos) : SDR_DC_TILE;   // < 32 only at the end of the stream
+    const int m = (L.b1 - pos < TILE) ? (int)(L.b1 - pos) : TILE;   // < 32 only at the end of the stream
 #pragma unroll
-    for (int q = 0; q < SDR_DC_TILE / 4; q++) {
+    for (int q = 0; q < TILE / 4; q++) {
         const float4 v = rd.get4(q);
         float4       y;
         if (4 * q + 0 < m) { o = dc_exact<MODE>(v.x, l, o); l = v.x; } y.x = o;
@@ -208,7 +209,7 @@ SDR_HD bool dc_lane_tile(const DcArgs &A, long long c, DcLane &L, const Rd &rd, 
         wr.put4(q, y);
     }
     L.l = l; L.o = o;
-    if (pos + SDR_DC_TILE >= L.b1) A.fin[c] = dc_bits(o);
+    if (pos + TILE >= L.b1) A.fin[c] = dc_bits(o);
     return true;
 }
 
@@ -235,14 +236,14 @@ struct DcMemWriter {
 // The whole walk of chunk c straight out of / into global memory: the kernel for buffers that are not 16-byte aligned,
 // and what the CPU tests run (tests/emul/dc_emul.cpp).  The aligned kernel (k_dc_spec_tiles) makes the same calls with
 // rows staged through shared memory by coalesced asynchronous copies.
-template <int MODE> SDR_HD void dc_chunk(const DcArgs &A, long long c) {
+template <int MODE, int TILE = 32> SDR_HD void dc_chunk(const DcArgs &A, long long c) {
     DcLane L;
     dc_lane_init(A, c, L);
-    const long long tiles = dc_lane_tiles(A);
+    const long long tiles = dc_lane_tiles<TILE>(A);
     for (long long t = 0; t < tiles; t++) {
         const DcMemReader rd = {A.in, L.pos, A.n};
         DcMemWriter       wr = {A.out, L.pos, L.b1};
-        dc_lane_tile<MODE>(A, c, L, rd, wr);
+        dc_lane_tile<MODE, TILE>(A, c, L, rd, wr);
     }
 }
 

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(32) k_dc_blocker(float last_sample, float last
 // Speculative pass, buffers with any 4-byte alignment: one lane per chunk, straight out of global memory.
 __global__ void __launch_bounds__(128) k_dc_spec(DcArgs A) {
     const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (c < A.chunks) dc_chunk<DC_NATIVE_ALL>(A, c);
+    if (c < A.chunks) dc_chunk<DC_NATIVE_ALL, 32>(A, c);
 }
 
 // Speculative pass, 16-byte aligned buffers.  A warp owns 32 consecutive chunks, one per lane, and all its lanes sit at
@@ -54,10 +54,6 @@ __global__ void __launch_bounds__(128) k_dc_spec(DcArgs A) {
 // per-lane version above reads 32 separate sectors per warp instruction, each in its own DRAM page: ncu showed it
 // waiting on memory (long_scoreboard 5.4 warps per issue at 19 % of DRAM bandwidth).
 namespace {
-constexpr int DC_ROW = 36;                      // floats per staged row (32 + 4 padding)
-constexpr int DC_NBUF = 3;                      // input tiles in flight per warp
-constexpr int DC_WARPS = 2;                     // warps per block
-constexpr int DC_TILE_FLOATS = 32 * DC_ROW;
 __device__ __forceinline__ void dc_cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -73,56 +69,64 @@ struct DcSmemWriter {
 };
 }  // namespace
 
-template <int MODE> __global__ void __launch_bounds__(32 * DC_WARPS, 6) k_dc_spec_tiles(DcArgs A) {
-    __shared__ __align__(16) float s_in[DC_WARPS][DC_NBUF][DC_TILE_FLOATS];
-    __shared__ __align__(16) float s_out[DC_WARPS][DC_TILE_FLOATS];
+// TILE samples (128 or 256 bytes) of each of the warp's 32 chunks per staged tile; WARPS warps per block.  A row holds
+// TILE + 4 floats: an odd number of 16-byte chunks, so the eight lanes of an LDS.128 phase hit eight distinct bank groups.
+// NBUF input tiles per warp, NBUF - 1 of them in flight ahead of the arithmetic.
+template <int MODE, int TILE, int WARPS, int NBUF>
+__global__ void __launch_bounds__(32 * WARPS) k_dc_spec_tiles(DcArgs A) {
+    constexpr int ROW = TILE + 4, TILE_FLOATS = 32 * ROW;
+    constexpr int PIECES = TILE / 4;          // 16-byte pieces per row
+    constexpr int ROWS_PER_INSTR = 32 / PIECES, INSTRS = 32 / ROWS_PER_INSTR;
+    static_assert((ROW / 4) % 2 == 1 && 32 % PIECES == 0, "row stride / copy geometry");
+    __shared__ __align__(16) float s_in[WARPS][NBUF][TILE_FLOATS];
+    __shared__ __align__(16) float s_out[WARPS][TILE_FLOATS];
     const int       lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long c_first = ((long long)blockIdx.x * DC_WARPS + warp) * 32;   // this warp's first chunk
+    const long long c_first = ((long long)blockIdx.x * WARPS + warp) * 32;   // this warp's first chunk
     if (c_first >= A.chunks) return;
     const long long c = c_first + lane;
-    const long long tiles = dc_lane_tiles(A);
-    const long long rel0 = -(long long)A.k1 - A.k2;        // offset of tile 0 from the start of a chunk
-    const int       sub_row = lane >> 3, piece = lane & 7;   // this lane's part in the cooperative copies
+    const long long tiles = dc_lane_tiles<TILE>(A);
+    const long long rel0 = -(long long)A.k1 - A.k2;                  // offset of tile 0 from the start of a chunk
+    const int       sub_row = lane / PIECES, piece = lane % PIECES;  // this lane's part in the cooperative copies
     DcLane L;
     dc_lane_init(A, c, L);
 
-    // copy tile t of all 32 chunks: instruction j moves one 16-byte piece of rows 4j .. 4j+3
+    // copy tile t of all 32 chunks: instruction j moves one 16-byte piece of ROWS_PER_INSTR rows
     auto issue = [&](long long t) {
         if (t < tiles) {
-            float *buf = s_in[warp][t % DC_NBUF];
+            float *buf = s_in[warp][t % NBUF];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int       row = 4 * j + sub_row;
+            for (int j = 0; j < INSTRS; j++) {
+                const int       row = ROWS_PER_INSTR * j + sub_row;
                 const long long cr = c_first + row;
-                const long long e = cr * A.ch + rel0 + t * SDR_DC_TILE + piece * 4;   // first element of the piece
-                long long       left = A.n - e;                                       // elements of it inside the stream
+                const long long e = cr * A.ch + rel0 + t * TILE + piece * 4;   // first element of the piece
+                long long       left = A.n - e;                                // elements of it inside the stream
                 if (cr < A.chunks && e >= 0 && left > 0)
-                    dc_cp_async16((uint32_t)__cvta_generic_to_shared(buf + row * DC_ROW + piece * 4), A.in + e,
+                    dc_cp_async16((uint32_t)__cvta_generic_to_shared(buf + row * ROW + piece * 4), A.in + e,
                                   left >= 4 ? 16u : (uint32_t)left * 4u);
             }
         }
         dc_cp_commit();
     };
-    issue(0);
-    issue(1);
+#pragma unroll
+    for (int t = 0; t < NBUF - 1; t++) issue(t);
     for (long long t = 0; t < tiles; t++) {
-        issue(t + 2);
-        dc_cp_wait<2>();
+        issue(t + NBUF - 1);
+        dc_cp_wait<NBUF - 1>();
         __syncwarp();
-        const DcSmemReader rd = {reinterpret_cast<const float4 *>(s_in[warp][t % DC_NBUF] + lane * DC_ROW)};
-        DcSmemWriter       wr = {reinterpret_cast<float4 *>(s_out[warp] + lane * DC_ROW)};
-        dc_lane_tile<MODE>(A, c, L, rd, wr);
+        const DcSmemReader rd = {reinterpret_cast<const float4 *>(s_in[warp][t % NBUF] + lane * ROW)};
+        DcSmemWriter       wr = {reinterpret_cast<float4 *>(s_out[warp] + lane * ROW)};
+        dc_lane_tile<MODE, TILE>(A, c, L, rd, wr);
         // owned tiles: every lane of the warp is in its owned range at the same time (the phase depends on the offset only)
-        if (rel0 + t * SDR_DC_TILE >= 0) {
+        if (rel0 + t * TILE >= 0) {
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int       rw = 4 * j + sub_row;
+            for (int j = 0; j < INSTRS; j++) {
+                const int       rw = ROWS_PER_INSTR * j + sub_row;
                 const long long cr = c_first + rw;
-                const long long e = cr * A.ch + rel0 + t * SDR_DC_TILE + piece * 4;
+                const long long e = cr * A.ch + rel0 + t * TILE + piece * 4;
                 const long long left = A.n - e;
                 if (cr < A.chunks && left > 0) {
-                    const float4 v = *reinterpret_cast<const float4 *>(s_out[warp] + rw * DC_ROW + piece * 4);
+                    const float4 v = *reinterpret_cast<const float4 *>(s_out[warp] + rw * ROW + piece * 4);
                     if (left >= 4) *reinterpret_cast<float4 *>(A.out + e) = v;
                     else { A.out[e] = v.x; if (left > 1) A.out[e + 1] = v.y; if (left > 2) A.out[e + 2] = v.z; }
                 }
@@ -176,9 +180,9 @@ static void dc_tuning(const Ctx *c, long long n, int *ch, int *k1, int *k2) {
         if (per > 8192) per = 8192;
         want = (int)per;
     }
-    *ch = (want + 31) & ~31;
-    *k1 = (*k1 + 31) & ~31;
-    *k2 = (*k2 + 31) & ~31;
+    *ch = (want + 63) & ~63;   // multiples of the larger tile
+    *k1 = (*k1 + 63) & ~63;
+    *k2 = (*k2 + 63) & ~63;
 }
 
 static bool overlap(const void *a, const void *b, size_t bytes) {
@@ -217,12 +221,14 @@ static int dc_run(Ctx *c, float last_sample, float last_output, const float *d_s
     A.fail_bits = A.fin + A.chunks;
     A.final2 = d_final2;
     const bool vec = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
-    const int grid_t = (int)((A.chunks + 32 * DC_WARPS - 1) / (32 * DC_WARPS));
-    static const int mode = env_int("SDR_B200_DC_MODE", DC_NATIVE_ALL);   // measurement knob: the flavours give identical bits
-    if (vec && mode == DC_WIDEN_BOTH)       k_dc_spec_tiles<DC_WIDEN_BOTH><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
-    else if (vec && mode == DC_WIDEN_DIFF)  k_dc_spec_tiles<DC_WIDEN_DIFF><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
-    else if (vec && mode == DC_NATIVE)      k_dc_spec_tiles<DC_NATIVE><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
-    else if (vec)                           k_dc_spec_tiles<DC_NATIVE_ALL><<<grid_t, 32 * DC_WARPS, 0, c->s()>>>(A);
+    static const int mode = env_int("SDR_B200_DC_MODE", DC_NATIVE_ALL);   // measurement knobs: every flavour gives identical bits
+    static const int tile = env_int("SDR_B200_DC_TILE", 32);
+    const int g2 = (int)((A.chunks + 63) / 64), g1 = (int)((A.chunks + 31) / 32);
+    if (vec && tile == 64)                  k_dc_spec_tiles<DC_NATIVE_ALL, 64, 1, 2><<<g1, 32, 0, c->s()>>>(A);
+    else if (vec && mode == DC_WIDEN_BOTH)  k_dc_spec_tiles<DC_WIDEN_BOTH, 32, 2, 3><<<g2, 64, 0, c->s()>>>(A);
+    else if (vec && mode == DC_WIDEN_DIFF)  k_dc_spec_tiles<DC_WIDEN_DIFF, 32, 2, 3><<<g2, 64, 0, c->s()>>>(A);
+    else if (vec && mode == DC_NATIVE)      k_dc_spec_tiles<DC_NATIVE, 32, 2, 3><<<g2, 64, 0, c->s()>>>(A);
+    else if (vec)                           k_dc_spec_tiles<DC_NATIVE_ALL, 32, 2, 3><<<g2, 64, 0, c->s()>>>(A);
     else     k_dc_spec<<<(int)((A.chunks + 127) / 128), 128, 0, c->s()>>>(A);
     SDR_LAUNCH_CHECK(c);
     k_dc_repair<<<1, 1024, 0, c->s()>>>(A);
@@ -263,7 +269,7 @@ int sdr_dev_dc_blocker(sdr_ctx_t *ctx, float last_sample, float last_output, con
 int sdr_dc_blocker_tuning(sdr_ctx_t *ctx, int chunk, int cheap_warmup, int exact_warmup, long long min_parallel) {
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c) return set_error(SDR_EINVAL, "sdr_dc_blocker_tuning: null context");
-    if (chunk > 0 && chunk < 32) return set_error(SDR_EINVAL, "sdr_dc_blocker_tuning: chunk %d < 32", chunk);
+    if (chunk > 0 && chunk < 64) return set_error(SDR_EINVAL, "sdr_dc_blocker_tuning: chunk %d < 64", chunk);
     c->dc_chunk = chunk; c->dc_k1 = cheap_warmup; c->dc_k2 = exact_warmup; c->dc_min_parallel = min_parallel;
     return SDR_OK;
 }

@@ -9,8 +9,8 @@
 using namespace sdr;
 
 extern "C" int emul_dc_blocker(const float *in, float *out, long long n, float last_sample, float last_output, int ch,
-                               int k1, int k2, int vec, int reverse_chunks, float *final2, unsigned long long *stats) {
-    if (n <= 0 || ch < 32 || (ch & 31) || (k1 & 31) || (k2 & 31)) return 1;
+                               int k1, int k2, int vec, int reverse_chunks, float *final2, unsigned long long *stats, int tile) {
+    if (n <= 0 || (tile != 32 && tile != 64) || ch < tile || (ch % tile) || (k1 % tile) || (k2 % tile)) return 1;
     DcArgs A;
     A.in = in; A.out = out; A.n = n;
     A.last_sample = last_sample; A.last_output = last_output; A.state_in = nullptr;
@@ -22,9 +22,13 @@ extern "C" int emul_dc_blocker(const float *in, float *out, long long n, float l
     // the lanes of the kernel run in no particular order
     for (long long i = 0; i < A.chunks; i++) {
         const long long c = reverse_chunks ? A.chunks - 1 - i : i;
-        // `vec` selects the arithmetic flavour here (0 widen both, 1 widen the difference, 2 native, 3 native incl. the cheap warm-up): identical bits
-        if (vec == 0) dc_chunk<DC_WIDEN_BOTH>(A, c); else if (vec == 1) dc_chunk<DC_WIDEN_DIFF>(A, c);
-        else if (vec == 2) dc_chunk<DC_NATIVE>(A, c); else dc_chunk<DC_NATIVE_ALL>(A, c);
+        // `vec` selects the arithmetic flavour here (0 widen both, 1 widen the difference, 2 native, 3 native incl. the
+        // cheap warm-up), `tile` the walk granularity: identical bits for all of them
+        if (tile == 64) dc_chunk<DC_NATIVE_ALL, 64>(A, c);
+        else if (vec == 0) dc_chunk<DC_WIDEN_BOTH, 32>(A, c);
+        else if (vec == 1) dc_chunk<DC_WIDEN_DIFF, 32>(A, c);
+        else if (vec == 2) dc_chunk<DC_NATIVE, 32>(A, c);
+        else dc_chunk<DC_NATIVE_ALL, 32>(A, c);
     }
     bool any = false;
     for (long long c = 1; c < A.chunks; c++)

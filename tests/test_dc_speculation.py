@@ -32,7 +32,7 @@ def emul():
     lib = C.CDLL(OUT)
     lib.emul_dc_blocker.restype = C.c_int
     lib.emul_dc_blocker.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
-                                    C.c_int, C.c_void_p, C.c_void_p]
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     return lib
 
 
@@ -42,7 +42,7 @@ def aligned(n, offset_floats=0):
     return raw[skew + offset_floats: skew + offset_floats + n]
 
 
-def run(lib, x, s0=0.0, o0=0.0, ch=2048, k1=6144, k2=4096, vec=2, reverse=0, offset=0):
+def run(lib, x, s0=0.0, o0=0.0, ch=2048, k1=6144, k2=4096, vec=2, reverse=0, offset=0, tile=32):
     xin = aligned(len(x), offset)
     xin[:] = x
     out = aligned(len(x), offset)
@@ -50,7 +50,7 @@ def run(lib, x, s0=0.0, o0=0.0, ch=2048, k1=6144, k2=4096, vec=2, reverse=0, off
     fin = np.zeros(2, np.float32)
     stats = np.zeros(4, np.uint64)
     assert lib.emul_dc_blocker(xin.ctypes.data, out.ctypes.data, len(x), s0, o0, ch, k1, k2, vec, reverse, fin.ctypes.data,
-                               stats.ctypes.data) == 0
+                               stats.ctypes.data, tile) == 0
     return out, fin, stats
 
 
@@ -87,6 +87,15 @@ def test_ragged_lengths_and_chunk_sizes(emul, port):
     for n in (1, 7, 8, 9, 1023, 1024, 1025, 4099, 70_001):
         for ch in (32, 64, 992, 1024):
             check(emul, port, noise(n, seed=n), 0.1, 0.2, ch=ch, k1=64, k2=512)
+
+
+def test_64_sample_tiles(emul, port):
+    """the walk in 256-byte tiles (SDR_B200_DC_TILE=64 on the device): same bits"""
+    x = noise(300_001, seed=8)
+    check(emul, port, x, 0.25, -0.5, ch=2048, tile=64)
+    check(emul, port, x, 0.25, -0.5, ch=4096, k1=0, k2=64, tile=64)
+    for n in (1, 63, 64, 65, 4099):
+        check(emul, port, x[:n], 0.1, 0.2, ch=64, k1=64, k2=512, tile=64)
 
 
 def test_scalar_access_path_and_lane_order(emul, port):
