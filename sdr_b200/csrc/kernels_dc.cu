@@ -222,7 +222,7 @@ static int dc_run(Ctx *c, float last_sample, float last_output, const float *d_s
     A.final2 = d_final2;
     const bool vec = (((uintptr_t)d_in | (uintptr_t)d_out) & 15) == 0;
     static const int mode = env_int("SDR_B200_DC_MODE", DC_NATIVE_ALL);   // measurement knobs: every flavour gives identical bits
-    static const int tile = env_int("SDR_B200_DC_TILE", 32);
+    static const int tile = env_int("SDR_B200_DC_TILE", 64);   // 256-byte tiles: 338 vs 311 Gsamples/s at 2^28 samples
     const int g2 = (int)((A.chunks + 63) / 64), g1 = (int)((A.chunks + 31) / 32);
     if (vec && tile == 64)                  k_dc_spec_tiles<DC_NATIVE_ALL, 64, 1, 2><<<g1, 32, 0, c->s()>>>(A);
     else if (vec && mode == DC_WIDEN_BOTH)  k_dc_spec_tiles<DC_WIDEN_BOTH, 32, 2, 3><<<g2, 64, 0, c->s()>>>(A);
