@@ -120,7 +120,7 @@ SDR_HD double dc_cheap(double xd, double ld, double a) {
 }
 
 // ---- one lane's walk over its chunk, in tiles of TILE samples ----------------------------------------------------------
-// A lane visits positions [b0 - K1 - K2, b1) of the stream in 32-sample tiles (chunk and warm-up lengths are multiples
+// A lane visits positions [b0 - K1 - K2, b1) of the stream in TILE-sample tiles (chunk and warm-up lengths are multiples
 // of the tile, so a tile lies in exactly one phase and every lane of a warp is in the same phase at the same time):
 //   cheap warm-up  [b0 - K1 - K2, b0 - K2)   double state, one DFMA per sample
 //   exact warm-up  [b0 - K2, b0)             the reference's arithmetic, nothing stored

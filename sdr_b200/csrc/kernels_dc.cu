@@ -47,12 +47,12 @@ __global__ void __launch_bounds__(128) k_dc_spec(DcArgs A) {
 }
 
 // Speculative pass, 16-byte aligned buffers.  A warp owns 32 consecutive chunks, one per lane, and all its lanes sit at
-// the same offset inside their chunks.  Per 32-sample tile the warp copies one 128-byte line of each of its 32 chunks
-// into shared memory with coalesced 16-byte asynchronous copies (8 lanes per line, 4 lines per instruction, two tiles
-// ahead of the arithmetic: a tile is ~2500 cycles of dependent arithmetic per lane, which is what hides DRAM), every
-// lane then reads ITS row (row stride 36 floats: conflict-free LDS.128), and the outputs go back the same way.  The
-// per-lane version above reads 32 separate sectors per warp instruction, each in its own DRAM page: ncu showed it
-// waiting on memory (long_scoreboard 5.4 warps per issue at 19 % of DRAM bandwidth).
+// the same offset inside their chunks.  Per tile the warp copies one TILE-sample piece (256 bytes by default) of each of
+// its 32 chunks into shared memory with coalesced 16-byte asynchronous copies (TILE/4 lanes per piece, ahead of the
+// arithmetic: a tile is ~4500 cycles of dependent arithmetic per lane, which is what hides DRAM), every lane then reads
+// ITS row with conflict-free LDS.128, and the outputs go back the same way.  The per-lane version above reads 32
+// separate sectors per warp instruction, each in its own DRAM page: ncu showed it waiting on memory (long_scoreboard
+// 5.4 warps per issue at 19 % of DRAM bandwidth).
 namespace {
 __device__ __forceinline__ void dc_cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
