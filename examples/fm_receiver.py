@@ -52,7 +52,12 @@ def main():
     front.connect(resampler).connect(audio).connect(volume)   # >-> on the device
 
     # vectors of 16384 bytes = 8192 IQ pairs, like the reference's 8192-sample buffers (fm.hs:24)
-    st = sdr_b200.serialize.runHandles(front, volume, 16384, fin, fout)
+    try:
+        st = sdr_b200.serialize.runHandles(front, volume, 16384, fin, fout)
+    except sdr_b200.SdrError as e:
+        # a recording whose tail is shorter than the decimator's 128 taps trips the reference's own `decimate 1`
+        # assert (Filter.hs:586) -- after everything before it has been processed and written
+        sys.exit(f"stopped at the end of the input: {e.msg}")
     print(f"{st.elements_in // 2} IQ samples in, {st.elements_out} audio samples out "
           f"(read {st.read_seconds:.3f} s, write {st.write_seconds:.3f} s)", file=sys.stderr)
 
