@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run on the GPU box with -m gpu)")
+    config.addinivalue_line("markers", "timeout: per-test limit (pytest-timeout; inert when the plugin is absent)")
 
 
 @pytest.fixture(scope="session")

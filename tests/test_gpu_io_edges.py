@@ -12,7 +12,7 @@ import pytest
 
 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180)]
 
 
 @pytest.fixture(scope="module")
@@ -93,12 +93,16 @@ def test_os_pipe_source_with_partial_reads(sdr):
 
     def produce():
         b, i, k = x.tobytes(), 0, 0
-        while i < len(b):
-            step = (1000, 7, 16384, 333, 65536)[k % 5]
-            os.write(w, b[i:i + step])
-            i += step
-            k += 1
-        os.close(w)
+        try:
+            while i < len(b):
+                step = (1000, 7, 16384, 333, 65536)[k % 5]
+                os.write(w, b[i:i + step])
+                i += step
+                k += 1
+        except OSError:
+            pass   # the reader went away (a failed run): the assertion below reports it
+        finally:
+            os.close(w)
     got = []
 
     def consume():
@@ -113,9 +117,10 @@ def test_os_pipe_source_with_partial_reads(sdr):
     try:
         st = sdr.serialize.runHandles(head, sink, 4096, r, w2)
     finally:
-        os.close(w2)
-        tp.join(); tc.join()
-        os.close(r); os.close(r2)
+        # close our ends first: if the run failed early the producer must get EPIPE and the consumer EOF, never block
+        os.close(r); os.close(w2)
+        tp.join(30); tc.join(30)
+        os.close(r2)
     out = np.frombuffer(b"".join(got), np.float32)
     assert st.vectors_in == 21
     assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
