@@ -145,3 +145,31 @@ def test_special_values(emul, port):
     x = (np.random.default_rng(4).integers(0, 256, 90_000).astype(np.float32) - 128) / 128   # converted u8 samples
     st = check(emul, port, x, ch=1024)
     assert st[2] == 0
+
+
+def test_property_any_input_any_tuning_is_bit_exact(emul, port):
+    """hypothesis: whatever the length, the state, the chunk / warm-up lengths, the tile, the arithmetic flavour and the
+    input (noise, constant stretches, zeros, denormals, huge values mixed), the chunk-parallel evaluation equals the
+    reference recurrence bit for bit"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40_000), st.sampled_from([64, 128, 320, 1024, 4096]), st.sampled_from([0, 64, 512, 2048]),
+           st.sampled_from([0, 64, 256, 1024]), st.sampled_from([32, 64]), st.integers(0, 3), st.integers(0, 2 ** 31 - 1),
+           st.floats(-4, 4, width=32), st.floats(-4, 4, width=32))
+    def prop(n, ch, k1, k2, tile, flavour, seed, s0, o0):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal(n).astype(np.float32)
+        kind = seed % 5
+        if kind == 1:                                   # constant stretches (fixed points of the recurrence)
+            x[n // 3: 2 * n // 3] = x[n // 3]
+        elif kind == 2:                                 # zeros and denormals
+            x[::3] = 0.0
+            x[1::7] *= np.float32(1e-42)
+        elif kind == 3:                                 # huge dynamic range
+            x *= np.exp(rng.uniform(-40, 40, n)).astype(np.float32)
+        elif kind == 4:                                 # the u8 sample grid
+            x = ((rng.integers(0, 256, n).astype(np.float32) - 128) / 128).astype(np.float32)
+        check(emul, port, x, s0, o0, ch=ch, k1=k1, k2=k2, vec=flavour, tile=tile)
+
+    prop()
