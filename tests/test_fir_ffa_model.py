@@ -66,3 +66,30 @@ def test_ffa_random_taps_and_large_dynamic_range(emul, port):
     gi = ffa(emul, ti, xi)
     wi = port.filter(oracle.V_AVX, len(gi), ti, xi, False)
     assert np.array_equal(gi, wi)
+
+
+def test_property_random_taps_and_streams(emul, port):
+    """hypothesis, shapes like the reference's QuickCheck generators (values in (-10, 10), symmetric taps): inside the
+    path's tolerance against the reference AVX filter, and an identity on integer data"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.sampled_from([32, 64]), st.integers(200, 20_000), st.integers(0, 2 ** 31 - 1), st.booleans())
+    def prop(T, n, seed, integers):
+        rng = np.random.default_rng(seed)
+        if integers:
+            half = rng.integers(-8, 9, T // 2).astype(np.float32)
+            x = rng.integers(-64, 65, n).astype(np.float32)
+        else:
+            half = rng.uniform(-10, 10, T // 2).astype(np.float32)
+            x = rng.uniform(-10, 10, n).astype(np.float32)
+        taps = np.concatenate([half, half[::-1]])
+        got = ffa(emul, taps, x)
+        want = port.filter(oracle.V_AVX, len(got), taps, x, False)
+        if integers:
+            assert np.array_equal(got, want)
+        else:
+            scale = np.maximum(np.abs(want), np.sqrt(np.mean(want.astype(np.float64) ** 2)))
+            assert float((np.abs(got - want) / scale).max()) <= 1e-5
+
+    prop()
