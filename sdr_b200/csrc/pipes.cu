@@ -719,6 +719,12 @@ int sdr_pipe_run_fd(sdr_pipe_t *p, sdr_pipe_t *sink, int in_fd, long long vec_le
     SDR_TRY(p->ctx->bind());
     struct BoundGuard { BoundGuard() { g_bound = true; } ~BoundGuard() { g_bound = false; } } bound_guard;
     FdRun R;
+    // whatever way this function is left, no deferred or in-flight copy may still point into R's page-locked ring when
+    // it is freed (declared after R: runs before R's destructor)
+    struct Quiesce {
+        sdr_pipe *p;
+        ~Quiesce() { flush_pending(p); cudaStreamSynchronize(p->ctx->stream); cudaStreamSynchronize(p->ctx->side); }
+    } quiesce{p};
     const size_t vec_bytes = (size_t)vec_len * p->in_eb;
     // page-locked staging ring of two halves: read() lands directly in DMA-able memory; while one half is being
     // copied to the device the other one is being filled
