@@ -603,6 +603,12 @@ int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_
     SDR_TRY(p->ctx->bind());
     auto t_start = std::chrono::steady_clock::now();
     struct BoundGuard { BoundGuard() { g_bound = true; } ~BoundGuard() { g_bound = false; } } bound_guard;
+    // on an error return no deferred or in-flight copy may still point into the caller's vectors (a no-op after the
+    // final sdr_pipe_sync of the normal path)
+    struct Quiesce {
+        sdr_pipe *p; bool armed;
+        ~Quiesce() { if (armed) { flush_pending(p); cudaStreamSynchronize(p->ctx->stream); cudaStreamSynchronize(p->ctx->side); } }
+    } quiesce{p, true};
     for (long long v = 0; v < n_vecs; v++) {
         SDR_TRY(pipe_push_any(p, (const char *)in + (size_t)(v * vec_len) * p->in_eb, vec_len, in_mem));
         SDR_TRY(drain(sink, out, out_capacity, out_mem, &written));
@@ -619,6 +625,7 @@ int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_
         fprintf(stderr, "[sdr_b200 trace] sdr_pipe_run: host issue %.1f us, final sync %.1f us\n",
                 std::chrono::duration<double, std::micro>(t_issued - t_start).count(),
                 std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_issued).count());
+    quiesce.armed = false;   // sdr_pipe_sync above has done it
     *n_out = written;
     return SDR_OK;
 }
