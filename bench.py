@@ -188,6 +188,38 @@ def cpu_run(threads, seconds, n_vectors=4096):
                       f"{secs.value:.1f} s"}
 
 
+def cpu_run_u8(threads, seconds, n_vectors=16384):
+    """the reference's own CPU path for the u8-fed chain: convertCAVX (convert.c:37) + decimateAVXRC (decimate.c:105)
+    per 16384-byte vector, as `P.map interleavedIQUnsignedByteToFloatFast >-> firDecimator` issues them"""
+    import oracle
+    import synth
+    port = oracle.port()
+    ref = oracle.ref()
+    lib = port.lib
+    lib.o_bench_u8_fir_decimator.restype = C.c_double
+    lib.o_bench_u8_fir_decimator.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long,
+                                             C.c_int, C.c_int, C.c_double, C.POINTER(C.c_long), C.POINTER(C.c_double)]
+    if ref is not None:
+        conv, fn, kind = C.cast(ref.lib.convertCAVX, C.c_void_p), C.cast(ref.lib.decimateAVXRC, C.c_void_p), "reference"
+    else:
+        conv, fn, kind = C.cast(lib.o_convertC, C.c_void_p), C.cast(lib.o_port_decimateAVXRC, C.c_void_p), "port"
+    taps = design_taps()
+    dup = np.repeat(taps, 2).astype(np.float32)
+    n_vectors = max(n_vectors, threads * 8)
+    key = ("u8", n_vectors)
+    if key not in _CPU_STREAM:   # 256 MiB of bytes (DRAM-resident like the f32 sample): a 16 MiB piece of the counter stream, tiled
+        piece = synth.rand_bytes(1 << 24)
+        _CPU_STREAM[key] = np.tile(piece, (2 * BUF * n_vectors + len(piece) - 1) // len(piece))[:2 * BUF * n_vectors]
+    x = _CPU_STREAM[key]
+    done, secs = C.c_long(), C.c_double()
+    rate = lib.o_bench_u8_fir_decimator(conv, fn, FACTOR, TAPS, dup.ctypes.data, taps.ctypes.data, x.ctypes.data, n_vectors, BUF,
+                                        threads, seconds, C.byref(done), C.byref(secs))
+    return {"value": rate / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{done.value} input samples ({done.value // BUF} x {2 * BUF}-byte u8 IQ vectors from a {n_vectors}-vector "
+                      f"({n_vectors * BUF * 2 >> 20} MiB) stream; per vector convertCAVX + decimateAVXRC 1009 outputs + 15 crossover outputs) in "
+                      f"{secs.value:.1f} s"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -198,13 +230,23 @@ def run_reference(args, rank, world):
     vals = [cpu_run(threads, per_step) for _ in range(max(1, args.steps))]
     best = max(vals, key=lambda v: v["value"])
     mean = sum(v["value"] for v in vals) / len(vals)
+    # second record: the u8-fed chain (convertCAVX + decimateAVXRC), same threads, a bounded sample
+    u8 = None
+    try:
+        cpu_run_u8(threads, 0.3)
+        u8v = [cpu_run_u8(threads, per_step) for _ in range(min(3, max(1, args.steps)))]
+        u8 = dict(max(u8v, key=lambda v: v["value"]), value=sum(v["value"] for v in u8v) / len(u8v),
+                  h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    except Exception as e:   # an old prebuilt liboracle.so without the u8 driver
+        u8 = {"unavailable": str(e)}
     line = {"impl": "reference", "metric": METRIC, "value": mean, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(), "taps": TAPS, "decimation": FACTOR, "buffer": BUF,
                        "note": "each step is a bounded 2 s sample of the stream on all host threads"},
             "cpu_baseline": dict(best, value=mean),
-            "e2e": {"value": mean, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": mean, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e_u8": u8}
     print(json.dumps(line), flush=True)
 
 
@@ -216,12 +258,46 @@ def workload_name():
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+def timed_passes(ctx, comm, dist, world, fn, n_calls, sdr_b200):
+    """device time of n_calls back-to-back calls of fn on the library's stream.  All ranks are lined up IN-STREAM first
+    (a 4-byte ncclAllReduce on the same stream, sdr_comm_barrier): no rank's span contains another rank's host start-up."""
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+        comm.barrier()
+    e0, e1 = sdr_b200.Event(ctx), sdr_b200.Event(ctx)
+    e0.record()
+    for _ in range(n_calls):
+        fn()
+    e1.record()
+    ms = e0.elapsed_ms(e1)
+    e0.destroy(); e1.destroy()
+    return ms
+
+
+def gather_max(dist, world, ms):
+    """(max over ranks, per-rank list)"""
+    if world == 1:
+        return ms, [ms]
+    import torch
+    parts = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, torch.tensor([ms], dtype=torch.float64))
+    per = [float(p.item()) for p in parts]
+    return max(per), per
+
+
 def run_gpu(args, rank, world, local_rank, dist):
     import sdr_b200
     from sdr_b200 import _lib as L
     from sdr_b200 import multigpu
 
     n = 1 << args.log2n
+    K = max(1, args.passes if args.passes > 0 else 8 * world)
+    warmup = max(args.warmup, 3)
+    pin_rank_to_gpu_numa(local_rank)
+    # NVML is initialised and polling on EVERY rank before anything is timed (round 1 started it on rank 0 only, between
+    # the barrier and the first event: the other ranks' spans then contained rank 0's NVML start-up)
+    sampler = ClockSampler(local_rank)
     ctx = sdr_b200.Context(local_rank)
     taps = design_taps()
     dec = sdr_b200.cudaDecimatorC(FACTOR, taps, ctx=ctx, sizeMultiple=4)
@@ -239,58 +315,69 @@ def run_gpu(args, rank, world, local_rank, dist):
     d_out = ctx.alloc(8 * max(plan.out_count, 1) + 256)
     ctx.synth_noise(d_in, 2 * plan.in_count, first_float=2 * plan.in_begin)
     ctx.sync()
-    halo = "none"
+
+    def step_pass():
+        multigpu.decimate_sharded(dec, comm, plan, d_in.ptr, d_out.ptr)
+
+    halo, nccl_ms_per_pass = "none", None
     if world > 1:
-        halo = "nccl send/recv per pass"
+        halo = "nccl send/recv per pass (side stream) + boundary launch"
+        # secondary figure: the NCCL transport (what north_star names), a few passes
         if args.halo == "peer":
+            for _ in range(3):
+                step_pass()
+            ms_n = timed_passes(ctx, comm, dist, world, step_pass, 4 * K, sdr_b200)
+            nccl_ms_per_pass = gather_max(dist, world, ms_n)[0] / (4 * K)
             dist.barrier()   # every chunk complete before a neighbour may read it
             try:
                 comm.share_chunks(d_in.ptr)
-                halo = "peer memory (CUDA IPC over NVLink), read in place by the boundary launch"
+                halo = ("peer memory: the ring kernel's edge fills read the T-D halo samples in place from the right neighbour's "
+                        "HBM over NVLink (CUDA IPC mapping, TMA bulk copies); one launch per pass, no rendezvous")
             except sdr_b200.SdrError as e:
                 if rank == 0:
                     print(f"peer-memory halo unavailable ({e}); using NCCL", file=sys.stderr)
 
-    def barrier():
-        ctx.sync()
-        if world > 1:
-            dist.barrier()
-            ctx.sync()
-
-    def step():
-        multigpu.decimate_sharded(dec, comm, plan, d_in.ptr, d_out.ptr)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = sdr_b200.Event(ctx), sdr_b200.Event(ctx)
+    for _ in range(warmup * K):
+        step_pass()
     launches0 = ctx.launches
     t_wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    ms = e0.elapsed_ms(e1)
-    barrier()
+    ms = timed_passes(ctx, comm, dist, world, step_pass, args.steps * K, sdr_b200)
+    ctx.sync()
     t_wall1 = time.time()
     launches = ctx.launches - launches0
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     kernel_name = dec.last_kernel()
-
-    # max over ranks (device time)
+    ms_max, ms_ranks = gather_max(dist, world, ms)
+    clocks = sampler.stop(t_wall0, t_wall1)
     if world > 1:
         import torch
-        t = torch.tensor([ms], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
         tl = torch.tensor([launches], dtype=torch.int64)
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
         launches_total = int(tl.item())
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        if rank == 0 and clocks is not None:
+            clocks["per_rank_sm_mhz"] = [c.get("sm_mhz") if c else None for c in allc]
+            rs = set(clocks.get("reasons", []))
+            for c in allc:
+                rs |= set((c or {}).get("reasons", []))
+            clocks["reasons"] = sorted(rs)
     else:
-        ms_max, launches_total = ms, launches
+        launches_total = launches
     ms_per_step = ms_max / args.steps
-    value = n / (ms_per_step * 1e-3) / 1e6
+    ms_per_pass = ms_per_step / K
+    value = n * K / (ms_per_step * 1e-3) / 1e6
+
+    # the same pass WITHOUT the exchange (interior outputs of the resident chunk only): what the halo costs
+    halo_ms = None
+    if world > 1:
+        def interior_pass():
+            L.check(L.lib.sdr_decimate_stream(dec.handle, d_in.ptr, plan.in_count, d_out.ptr, plan.out_interior))
+        for _ in range(3):
+            interior_pass()
+        ms_i = timed_passes(ctx, comm, dist, world, interior_pass, 4 * K, sdr_b200)
+        halo_ms = ms_per_pass - gather_max(dist, world, ms_i)[0] / (4 * K)
+        for _ in range(2):   # leave d_out holding the sharded result for the checksum
+            step_pass()
 
     # size-independent parity property at full size: checksum of all shards' outputs == rank-independent value
     csum = ctx.checksum32(d_out, 2 * plan.out_count, first_word=2 * plan.out_begin)
@@ -302,45 +389,71 @@ def run_gpu(args, rank, world, local_rank, dist):
         csum = sum(int(p[0]) + (int(p[1]) << 32) for p in parts) & 0xffffffffffffffff
 
     # ---- end to end through the Pipes boundary with host buffers (this rank's share of the stream + its halo) ----
-    e2e, e2e_spot = None, None
+    e2e, e2e_spot, e2e_u8 = None, None, None
     if not args.no_e2e:
         r = run_e2e(args, ctx, dec, plan, rank, world, dist, sdr_b200, L)
         if r is not None:
             e2e, e2e_spot = r
+        e2e_u8 = run_e2e_u8(args, ctx, dec, plan, rank, world, dist, sdr_b200, L)
 
-    # ---- roofline of the dominant kernel (rank 0's launch: its chunk / its time) ----
+    # ---- roofline of the dominant kernel, from the MAX-over-ranks time and the largest chunk ----
     peak, peak_src = measured_peak()
-    achieved = ALGO_BYTES_PER_SAMPLE * plan.in_count / ((ms / args.steps) * 1e-3) / 1e9
+    in_max = multigpu.shard_plan(n, TAPS, FACTOR, world, 0).in_count
+    achieved = ALGO_BYTES_PER_SAMPLE * in_max / (ms_per_pass * 1e-3) / 1e9
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ((traffic or {}).get("dram_bytes_per_input_sample") or 0) * plan.in_count or None,
+                "traffic": ((traffic or {}).get("dram_bytes_per_input_sample") or 0) * in_max or None,
                 "kernel": kernel_name, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * plan.in_count,
-                "note": "duration = CUDA events on the library's stream over the timed region / steps (ring kernel + ragged-tail launch)"}
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * in_max,
+                "launches_per_pass": launches / (args.steps * K),
+                "note": "per GPU: 9 B x the largest rank's chunk / (max-over-ranks device time per pass); the pass is ONE launch "
+                        "(ragged end and, sharded, the boundary windows are computed by the ring kernel itself)"}
     if traffic:
         roofline["traffic_source"] = traffic.get("source")
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_run(1, args.cpu_seconds)
+    cpu, configs, pipes_mode = None, None, None
+    if rank == 0 and world == 1:
+        if not args.no_configs:
+            d_in.free(); d_out.free()
+            configs = run_configs(args, ctx, dec, sdr_b200, L, peak)
+            pipes_mode = run_pipes_mode(args, ctx, dec, sdr_b200, L)
+        if not args.no_cpu:
+            cpu = cpu_run(1, args.cpu_seconds)
+            try:
+                if e2e is not None:
+                    e2e["spot_parity_vs_reference_avx"] = e2e_spot_parity(e2e_spot)
+            except Exception:
+                pass
+    elif world > 1 and e2e is not None:
+        # every rank checks 600 outputs of ITS OWN end-to-end run against the reference C; the line carries the AND
         try:
-            if e2e is not None:
-                e2e["spot_parity_vs_reference_avx"] = e2e_spot_parity(e2e_spot)
+            ok = e2e_spot_parity(e2e_spot) if not args.no_cpu else None
         except Exception:
-            pass
+            ok = None
+        oks = [None] * world
+        dist.all_gather_object(oks, ok)
+        e2e["spot_parity_vs_reference_avx"] = None if any(o is None for o in oks) else bool(all(oks))
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": workload_name() if args.log2n == LOG2_STREAM else f"reduced 2^{args.log2n}-sample stream (not the headline size)",
                            "taps": TAPS, "decimation": FACTOR, "buffer": BUF, "samples": n,
+                           "passes_per_step": K,
+                           "step": f"{K} back-to-back passes of the decimator over the whole 2^{args.log2n}-sample stream (8 x n_gpus: a step "
+                                   f"lasts ~3 ms at every N, the timed region is tens of ms even at 8 GPUs where one pass is ~50 us, and every N "
+                                   f"runs in the same power/clock regime); value = samples x passes / step time",
                            "l2": "inputs exceed L2 (per-GPU chunk %.0f MiB in + %.0f MiB out vs 126 MB L2)" % (
                                8 * plan.in_count / 2 ** 20, 8 * plan.out_count / 2 ** 20),
-                           "sharding": "single GPU" if world == 1 else f"{world} overlapping chunks, halo of {TAPS - FACTOR} samples per boundary via {halo}",
+                           "sharding": "single GPU" if world == 1 else f"{world} overlapping chunks, halo of {TAPS - FACTOR} samples per boundary: {halo}",
+                           "timing": "CUDA events on the library's stream after an in-stream ncclAllReduce lines the ranks up; max over ranks",
                            "arithmetic": "fp32 FMA, taps in increasing order; parity vs reference AVX path <= 1e-5 of output scale (tests/test_gpu_parity.py)",
                            "output_checksum": "%016x" % csum},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_total, "clocks": clocks}
+                "ms_per_pass": ms_per_pass, "ms_per_pass_by_rank": [m / (args.steps * K) for m in ms_ranks],
+                "halo_ms_per_pass": halo_ms, "nccl_halo_ms_per_pass": nccl_ms_per_pass,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_u8": e2e_u8, "configs": configs, "pipes_mode": pipes_mode,
+                "gpu_launches": launches_total, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if comm:
         comm.close()
@@ -423,11 +536,254 @@ def run_e2e(args, ctx, dec, plan, rank, world, dist, sdr_b200, L):
            "spot_parity_vs_reference_avx": None,
            "pcie_h2d_GBps_plain_memcpy": h2d_gbs,
            "h2d_GBps_achieved": 8.0 * (n_vecs * BUF) / (ms / steps * 1e-3) / 1e9,
+           "ceiling": {"value": h2d_gbs * 1e9 / 8.0 / 1e6 * (world if world > 1 else 1), "unit": UNIT,
+                       "what": "plain pinned cudaMemcpy host-to-device rate of this rank's link / 8 B per complex f32 sample"
+                               + (f", x {world} links" if world > 1 else "")
+                               + ": no kernel can make a host-fed f32 stream faster than this"},
            "bound": "PCIe host-to-device: 8 B per input sample must cross the link"}
     pipe.close()
     hin.free()
     hout.free()
     return res, spot
+
+
+def run_e2e_u8(args, ctx, dec, plan, rank, world, dist, sdr_b200, L):
+    """the same decimator fed with what an SDR front end delivers: u8 IQ host vectors (2 B per sample over the link)
+    through `P.map interleavedIQUnsignedByteToFloat >-> firDecimator` (examples/fm/fm.hs:34-36) as ONE fused stage
+    (sdr_pipe_u8_decimator), complex f32 host vectors out"""
+    n_local = plan.in_count + plan.halo
+    n_vecs = n_local // BUF
+    if n_vecs == 0:
+        return None
+    hin = sdr_b200.PinnedArray(np.uint8, 2 * n_vecs * BUF)
+    out_cap = (n_vecs * BUF // FACTOR // BUF + 1) * BUF
+    hout = sdr_b200.PinnedArray(np.float32, 2 * out_cap)
+    tmp = ctx.alloc(hin.array.nbytes)
+    ctx.synth_bytes(tmp, 2 * n_vecs * BUF, first_byte=2 * plan.in_begin)
+    L.check(L.lib.sdr_memcpy_d2h(ctx.h, hin.p, tmp.ptr, hin.array.nbytes))
+    ctx.sync()
+    tmp.free()
+    n_out = C.c_longlong()
+    pipe = sdr_b200.pipeU8Decimator(dec, BUF)
+    L.check(L.lib.sdr_pipe_set_batch(pipe.h, args.e2e_batch_vectors * BUF))
+
+    def one_pass():
+        L.check(L.lib.sdr_pipe_run(pipe.h, pipe.h, hin.p, 2 * BUF, n_vecs, L.SDR_HOST_PINNED, hout.p, out_cap, L.SDR_HOST_PINNED,
+                                   C.byref(n_out)))
+        return n_out.value
+
+    steps = max(1, min(args.steps, args.e2e_steps))
+    got = one_pass()
+    spot = None
+    if got >= 4096:
+        spot = {"first_output": 1000, "in_begin": int(plan.in_begin),
+                "y": np.array(hout.array[2 * 1000:2 * 1600], dtype=np.float32, copy=True),
+                "bytes": np.array(hin.array[2 * 1000 * FACTOR:2 * (1600 * FACTOR + TAPS)], dtype=np.uint8, copy=True)}
+    kernel = L.lib.sdr_pipe_last_kernel(pipe.h).decode()
+    one_pass()
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = sdr_b200.Event(ctx), sdr_b200.Event(ctx)
+    e0.record()
+    for _ in range(steps):
+        got = one_pass()
+    e1.record()
+    ms = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3)
+    if world > 1:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tn = torch.tensor([n_vecs * BUF], dtype=torch.int64)
+        dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+        total = int(tn.item())
+    else:
+        total = n_vecs * BUF
+    ok = None
+    if rank == 0 and not args.no_cpu and spot is not None:
+        try:
+            ok = e2e_u8_spot_parity(spot)
+        except Exception:
+            ok = None
+    res = {"value": total / (ms / steps * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(2 * n_vecs * BUF),
+           "d2h_bytes_per_step": int(8 * got), "steps": steps, "kernel": kernel,
+           "api": "sdr_pipe_run(sdr_pipe_u8_decimator = P.map interleavedIQUnsignedByteToFloat >-> firDecimator fused; 16384-byte "
+                  "pinned host u8 IQ vectors in, 8192-sample complex f32 host vectors out), "
+                  f"sdr_pipe_set_batch = {args.e2e_batch_vectors} output vectors per launch",
+           "workload": f"the headline stream as u8 IQ (what the RTL-SDR source yields, RTLSDRStream.hs:54-57): {n_vecs} x {BUF}-sample vectors per rank",
+           "spot_parity_vs_reference_convert_plus_avx": ok,
+           "link_GBps_achieved": (2.0 + 8.0 / FACTOR) * (n_vecs * BUF) / (ms / steps * 1e-3) / 1e9}
+    pipe.close()
+    hin.free()
+    hout.free()
+    return res
+
+
+def e2e_u8_spot_parity(spot):
+    """CPU leg: 600 outputs of the u8-fed end-to-end run against convertCAVX + decimateAVXRC of the same bytes"""
+    import oracle
+    ref = oracle.ref()
+    if ref is None:
+        return None
+    xs = ref.convert_u8("convertCAVX", spot["bytes"]).view(np.complex64)
+    want = ref.decimate("decimateAVXRC", 600, FACTOR, np.repeat(design_taps(), 2), xs)
+    got = spot["y"].view(np.complex64)
+    scale = np.maximum(np.abs(want), np.sqrt(np.mean(np.abs(want) ** 2)))
+    return bool(np.all(np.abs(got - want) <= 1e-5 * scale))
+
+
+# FP32 pipe peak measured on this pool's B200 (profiles/r01_mb_fma.txt, tools/mb_fma.cu: FFMA2 with a broadcast operand,
+# 67.1 TFLOP/s = 33.5 T lane-FMA/s); the secondary roofline of the FIR kernels
+FP32_PEAK_TFMA = 33.5
+
+
+def run_configs(args, ctx, dec, sdr_b200, L, peak):
+    """the other BASELINE.json configs and the element-wise stages, device resident, each with its own roofline"""
+    log2 = min(args.log2n, 27)
+    n = 1 << log2                                   # complex samples in the buffers (2n floats for the real kernels)
+    x = ctx.alloc(8 * n + 256)
+    y = ctx.alloc(8 * n + 256)
+    ctx.synth_noise(x, 2 * n)
+    out = {}
+
+    def timed(fn, steps=8, warm=3):
+        for _ in range(warm):
+            fn()
+        ctx.sync()
+        e0, e1 = sdr_b200.Event(ctx), sdr_b200.Event(ctx)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        ms = e0.elapsed_ms(e1) / steps
+        e0.destroy(); e1.destroy()
+        return ms
+
+    def put(key, what, ms, samples, bytes_per, fma_per, kernel, unit_name="input samples"):
+        rate = samples / (ms * 1e-3)
+        gbs = rate * bytes_per / 1e9
+        e = {"what": what, "ms": ms, "value": rate / 1e6, "unit": "Msamples/s", "samples_per_launch": samples, "kernel": kernel,
+             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                          "algorithmic_bytes_per_sample": bytes_per}}
+        if fma_per:
+            e["roofline"]["fp32_fma_per_sample"] = fma_per
+            e["roofline"]["fp32_frac"] = rate * fma_per / 1e12 / FP32_PEAK_TFMA
+            if e["roofline"]["fp32_frac"] > e["roofline"]["frac"]:
+                e["roofline"]["bound"] = "fp32 pipe (see fp32_frac; measured FFMA2 peak 33.5 TFMA/s)"
+        out[key] = e
+
+    nr = 2 * n
+    # cfg1: fastFilterSymR, 64 taps (32 half taps), real (Filter.hs:258-261 -> filter.c:60)
+    half = sdr_b200.windowed_sinc_taps(64, 1 / 4)[:32]
+    f = sdr_b200.cudaFilterSymR(half, ctx=ctx)
+    num = nr - 64 + 1
+    ms = timed(lambda: L.check(L.lib.sdr_filter_stream(f.handle, x.ptr, nr, y.ptr, num)))
+    put("cfg1", "fastFilterSymR 64-tap symmetric real FIR, 2^%d-sample real stream" % (log2 + 1), ms, nr, 8.0, 64, f.last_kernel())
+    # cfg3: fastResamplerR 3/10, 90 taps, real (Filter.hs:468-473 -> resample.c:70)
+    t_res = sdr_b200.windowed_sinc_taps(90, 1 / 20, gain=3.0)
+    r = sdr_b200.cudaResamplerR(3, 10, t_res, ctx=ctx, sizeMultiple=8)
+    num = (nr * 3 - r.numCoeffsR) // 10 + 1
+    ms = timed(lambda: L.check(L.lib.sdr_resample_stream(r.handle, x.ptr, nr, y.ptr, num)))
+    put("cfg3", "fastResamplerR 3/10 rational polyphase, 90 taps, 2^%d-sample real stream" % (log2 + 1), ms, nr, 5.2, 9, r.last_kernel())
+    # element-wise stages
+    nbytes = 2 * n
+    bbuf = ctx.alloc(nbytes + 256)
+    ctx.synth_bytes(bbuf, nbytes)
+    ms = timed(lambda: L.check(L.lib.sdr_dev_convert_u8(ctx.h, bbuf.ptr, y.ptr, nbytes)))
+    put("convert", "interleavedIQUnsignedByteToFloat (convert.c:37), per IQ pair", ms, n, 10.0, 0, "k_convert_u8_vec")
+    ms = timed(lambda: L.check(L.lib.sdr_dev_fm_demod(ctx.h, 0.0, 0.0, x.ptr, y.ptr, n)))
+    put("fmDemod", "fmDemod (Demod.hs:40), per complex sample", ms, n, 12.0, 0, "k_fm_demod4")
+    ms = timed(lambda: L.check(L.lib.sdr_dev_scale(ctx.h, 0.2, x.ptr, y.ptr, nr)))
+    put("scale", "scale (scale.c:30), per float", ms, nr, 8.0, 0, "k_scale_vec")
+    d_fin = ctx.alloc(8)
+    ms = timed(lambda: ctx.dc_blocker(x.ptr, y.ptr, nr, d_fin.ptr), steps=4, warm=2)
+    _, par = ctx.dc_stats()
+    put("dcBlocker", "dcBlocker (filter.c:152), chunk-parallel speculation, bit-exact, per float", ms, nr, 8.0, 0,
+        "k_dc_spec_tiles + k_dc_repair" if par else "k_dc_blocker")
+    d_fin.free()
+    # cfg4: the whole FM chain, u8 IQ in -> audio out, connected device pipes, 32 MiB pushes (16 Mi IQ pairs each)
+    fil = sdr_b200.cudaFilterSymR(half, ctx=ctx)
+    fe = sdr_b200.pipeFmFrontEnd(dec, BUF)
+    p3 = sdr_b200.pipeFirResampler(r, BUF)
+    p4 = sdr_b200.pipeFirFilter(fil, BUF)
+    p5 = sdr_b200.pipeScale(0.2, ctx)
+    fe.connect(p3).connect(p4).connect(p5)
+    for p in (fe, p3, p4):
+        L.check(L.lib.sdr_pipe_set_batch(p.h, 1 << 21))
+    n_out = C.c_longlong()
+    push = 1 << 25
+
+    def chain():
+        L.check(L.lib.sdr_pipe_run(fe.h, p5.h, bbuf.ptr, push, nbytes // push, L.SDR_DEVICE, y.ptr, 2 * n, L.SDR_DEVICE, C.byref(n_out)))
+    l0 = ctx.launches
+    ms = timed(chain, steps=4, warm=2)
+    put("cfg4_chain", "full FM pipe: u8 IQ -> convert -> decimate-by-8 (128 taps) -> fmDemod -> resample 3/10 (90 taps) -> 64-tap filter -> x0.2, "
+        "connected device pipes, 32 MiB pushes; per input IQ sample", ms, n, 2.15, 32 + 9 / 8 + 64 * 3 / 80, L.lib.sdr_pipe_last_kernel(fe.h).decode() + " + low-rate stages")
+    out["cfg4_chain"]["launches_per_pass"] = (ctx.launches - l0) / 6
+    out["cfg4_chain"]["audio_samples_out"] = int(n_out.value)
+    for p in (fe, p3, p4, p5):
+        p.close()
+    # the fused front end alone (u8 IQ -> phase)
+    fe = sdr_b200.pipeFmFrontEnd(dec, BUF)
+    L.check(L.lib.sdr_pipe_set_batch(fe.h, 1 << 23))
+
+    def front():
+        L.check(L.lib.sdr_pipe_run(fe.h, fe.h, bbuf.ptr, nbytes, 1, L.SDR_DEVICE, y.ptr, 2 * n, L.SDR_DEVICE, C.byref(n_out)))
+    ms = timed(front, steps=4, warm=2)
+    put("cfg4_front", "fused front end alone: u8 IQ -> convert -> decimate-by-8 -> fmDemod, one push", ms, n, 2.5, 32, L.lib.sdr_pipe_last_kernel(fe.h).decode())
+    fe.close()
+    for b in (bbuf, x, y):
+        b.free()
+    return out
+
+
+def run_pipes_mode(args, ctx, dec, sdr_b200, L):
+    """device-resident Pipes mode, vector by vector: 8192-sample SDR_DEVICE vectors pushed through firDecimator by the native
+    loop (sdr_pipe_run), launch threshold = 1 / 8 / 256 output vectors (sdr_pipe_set_batch)"""
+    n = 1 << min(args.log2n, 26)
+    x = ctx.alloc(8 * n + 256)
+    y = ctx.alloc(n + 8 * BUF + 256)
+    ctx.synth_noise(x, 2 * n)
+    res = {"vector": BUF, "samples": n, "unit": "Msamples/s"}
+    n_out = C.c_longlong()
+    for batch in (0, 8, 256):
+        pipe = sdr_b200.pipeFirDecimator(dec, BUF)
+        L.check(L.lib.sdr_pipe_set_batch(pipe.h, batch * BUF))
+
+        def run():
+            L.check(L.lib.sdr_pipe_run(pipe.h, pipe.h, x.ptr, BUF, n // BUF, L.SDR_DEVICE, y.ptr, n // FACTOR + BUF, L.SDR_DEVICE, C.byref(n_out)))
+        for _ in range(2):
+            run()
+        ctx.sync()
+        l0 = ctx.launches
+        t0 = time.perf_counter()
+        e0, e1 = sdr_b200.Event(ctx), sdr_b200.Event(ctx)
+        e0.record()
+        for _ in range(3):
+            run()
+        e1.record()
+        ms = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3) / 3
+        res[f"batch_{batch}"] = {"value": n / (ms * 1e-3) / 1e6, "ms": ms, "launches_per_pass": (ctx.launches - l0) / 3,
+                                 "input_vectors_per_launch": (n // BUF) / max(1.0, (ctx.launches - l0) / 3)}
+        pipe.close()
+    x.free(); y.free()
+    return res
+
+
+def pin_rank_to_gpu_numa(local_rank):
+    """bind this process to the CPUs NVML reports as local to its GPU BEFORE any page-locked memory is allocated (first
+    touch then places the pinned buffers on the GPU's NUMA node).  Best effort: silently a no-op where the topology is
+    not exposed (VMs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
 
 
 def e2e_spot_parity(spot):
@@ -452,8 +808,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2_STREAM, help="stream length (default 2^28, the headline workload)")
-    ap.add_argument("--halo", default="nccl", choices=["nccl", "peer"],
-                    help="multi-GPU halo transport: NCCL send/recv per pass (default) or in-place peer-memory reads")
+    ap.add_argument("--halo", default="peer", choices=["nccl", "peer"],
+                    help="multi-GPU halo transport: in-kernel peer-memory reads over NVLink (default; NCCL is timed beside it) "
+                         "or NCCL send/recv per pass")
+    ap.add_argument("--passes", type=int, default=0,
+                    help="back-to-back passes over the stream per step; default 8 x n_gpus, so that a step lasts ~3 ms at every N "
+                         "(one pass is ~0.36 ms on 1 GPU, ~0.05 ms on 8) and every N is measured in the same power/clock regime")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config / per-stage device-resident measurements")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)

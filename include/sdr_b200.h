@@ -17,7 +17,8 @@
  *
  * Conventions
  *   - Every function returns int status: 0 = SDR_OK, non-zero = error; sdr_last_error() gives the thread-local
- *     message.  The reference's C returns void and is UB on bad sizes; its Haskell side raises `error "filter 1"`
+ *     message.  (Layer 1: the reference's C returns void, so `IO ()` becomes `IO CInt`; the one family that already
+ *     returns a value, resample*, keeps it -- the next group -- and reports failure as a negative number.)  The reference's C returns void and is UB on bad sizes; its Haskell side raises `error "filter 1"`
  *     etc. on precondition failure (Filter.hs:525-527,544,586,691) -- the same preconditions are checked here
  *     and reported as SDR_EPRECOND with the reference's own location string.
  *   - Complex data is interleaved (re, im) float32, exactly as Data.Complex Float is laid out by
@@ -133,13 +134,14 @@ int decimateCudaRC(int num, int factor, int numCoeffs, const float *coeffs, cons
 int decimateCudaRCDup(int num, int factor, int numCoeffs, const float *coeffs, const float *inBuf, float *outBuf);
 int decimateCudaSymmetricRC(int num, int factor, int numCoeffs, const float *coeffs, const float *inBuf, float *outBuf);
 
-/* resample2RR/resampleSSERR/resampleAVXRR and resample2RC/resampleSSERC/resampleAVXRC (resample.c:34-142):
- * polyphase group tables exactly as FilterInternal.mkResampler builds them (:335-342).  *next_group receives the
- * value the C function returns (the next group index). */
-int resampleCudaRR(int buf_size, int num_coeffs, int starting_group, int num_groups, const int *increments,
-                   const float *const *coeffs, const float *in_buf, float *out_buf, int *next_group);
-int resampleCudaRC(int buf_size, int num_coeffs, int starting_group, int num_groups, const int *increments,
-                   const float *const *coeffs, const float *in_buf, float *out_buf, int *next_group);
+/* resample2RR/resampleSSERR/resampleAVXRR and resample2RC/resampleSSERC/resampleAVXRC (resample.c:34-142): the
+ * reference's EXACT signature -- polyphase group tables as FilterInternal.mkResampler builds them (:335-342), and the
+ * RETURN VALUE is the next group index (>= 0), which mkResampler's binding (:358-362) threads into the next call.
+ * Failure: -(SDR_E*) < 0, message in sdr_last_error(). */
+int resampleCudaRR(int buf_size, int num_coeffs, int starting_group, int num_groups, int *increments, float **coeffs,
+                   float *in_buf, float *out_buf);
+int resampleCudaRC(int buf_size, int num_coeffs, int starting_group, int num_groups, int *increments, float **coeffs,
+                   float *in_buf, float *out_buf);
 /* resampleRR (resample.c:16-32), legacy single-array form */
 int resampleCudaLegacyRR(int buf_size, int coeff_size, int interpolation, int decimation, int filter_offset,
                          const float *coeffs, const float *in_buf, float *out_buf);
@@ -280,6 +282,10 @@ int sdr_pipe_fm_demod(sdr_ctx_t *ctx, sdr_pipe_t **p);                          
  * stage: pushes are u8 IQ bytes (n = byte count, even), yields are vectors of block_size_out float phases.  Same
  * stream, bit for bit, as the three stages connected one after the other. */
 int sdr_pipe_fm_frontend(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **p);
+/* `P.map interleavedIQUnsignedByteToFloat >-> firDecimator d block_size_out` (fm.hs:34-36) as ONE fused stage: pushes are
+ * u8 IQ bytes (n = byte count, even), yields are vectors of block_size_out COMPLEX samples.  Same stream, bit for bit, as
+ * the two stages connected one after the other; the host link carries 2 B per input sample instead of 8. */
+int sdr_pipe_u8_decimator(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **p);
 const char *sdr_pipe_last_kernel(const sdr_pipe_t *p);
 int sdr_pipe_convert_u8(sdr_ctx_t *ctx, sdr_pipe_t **p); /* P.map interleavedIQUnsignedByteToFloat (Util.hs:104) */
 int sdr_pipe_scale(sdr_ctx_t *ctx, float factor, sdr_pipe_t **p);                   /* P.map (VG.map (* k)) fm.hs:40 */
@@ -349,11 +355,13 @@ typedef struct sdr_comm sdr_comm_t;
 int sdr_comm_unique_id(unsigned char id[SDR_COMM_ID_BYTES]);
 int sdr_comm_create(sdr_ctx_t *ctx, const unsigned char id[SDR_COMM_ID_BYTES], int world, int rank, sdr_comm_t **c);
 int sdr_comm_destroy(sdr_comm_t *c);
+/* in-stream rendezvous of all ranks: a 4-byte ncclAllReduce enqueued on the ctx stream (enqueue-only) */
+int sdr_comm_barrier(sdr_comm_t *c);
 /* Optional peer-memory transport for the halo (collective over the communicator): every rank passes the base address
  * of the sdr_dev_alloc allocation holding its chunk; CUDA IPC handles are exchanged with ncclAllGather and each rank
- * maps its right neighbour's chunk.  sdr_decimate_sharded on that same d_in then reads the T-D halo samples in place
- * from the neighbour's HBM over NVLink inside its boundary launch (no per-pass NCCL kernel).  The caller guarantees
- * the neighbour's chunk is complete before a pass starts. */
+ * maps its right neighbour's chunk.  sdr_decimate_sharded on that same d_in is then ONE launch: the ring kernel's edge
+ * fills read the T-D halo samples in place from the neighbour's HBM over NVLink (TMA bulk copies of peer memory; no
+ * per-pass NCCL kernel, no rendezvous).  The caller guarantees the neighbour's chunk is complete before a pass starts. */
 int sdr_comm_share_chunks(sdr_comm_t *c, const void *d_chunk_base);
 int sdr_comm_peer_halo_active(const sdr_comm_t *c, const void *d_in);
 /* one pass of the sharded decimator: interior outputs on the ctx stream, halo exchange (ncclSend of my first

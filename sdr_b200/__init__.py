@@ -9,6 +9,7 @@ from .filter import (Decimator, Filter, NativePipe, Resampler, cudaDecimatorC, c
                      cudaFilterC, cudaFilterR, cudaFilterSymR, cudaResamplerC, cudaResamplerR, default_context,
                      firDecimator, firFilter, firResampler, pipeFirDecimator, pipeFirFilter, pipeFirResampler)
 from .util import (complexFloatToInterleavedIQSigned2048, dcBlocker, dcBlockingFilter, fmDemod, pipeDcBlocker, fmDemodVec,  # noqa: F401
-                   interleavedIQSigned2048ToFloat, interleavedIQUnsignedByteToFloat, pipeConvertU8, pipeFmDemod, pipeFmFrontEnd,
+                   interleavedIQSigned2048ToFloat, interleavedIQUnsignedByteToFloat, pipeConvertU8, pipeFmDemod, pipeFmFrontEnd, pipeU8Decimator,
                    pipeScale, scaleFast)
+from .filterdesign import windowed_sinc_taps  # noqa: F401
 from . import multigpu, serialize  # noqa: F401

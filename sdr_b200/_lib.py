@@ -105,7 +105,7 @@ for _n in ("decimateCudaRR", "decimateCudaSymmetricRR", "decimateCudaRC", "decim
     _sig(_n, _I, _I, _I, _P, _P, _P)
 _sig("sdr_exact_decimate", _I, _I, _I, _I, _I, _P, _P, _P)
 for _n in ("resampleCudaRR", "resampleCudaRC"):
-    _sig(_n, _I, _I, _I, _I, _P, _P, _P, _P, C.POINTER(_I))
+    _sig(_n, _I, _I, _I, _I, _P, _P, _P, _P)   # returns the next group (>= 0) or -(status)
 _sig("sdr_exact_resample", _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, C.POINTER(_I))
 _sig("resampleCudaLegacyRR", _I, _I, _I, _I, _I, _P, _P, _P)
 _sig("convertCuda", _I, _P, _P)
@@ -151,6 +151,7 @@ _sig("sdr_pipe_fir_decimator", _P, _I, c_void_pp)
 _sig("sdr_pipe_fir_resampler", _P, _I, c_void_pp)
 _sig("sdr_pipe_fm_demod", _P, c_void_pp)
 _sig("sdr_pipe_fm_frontend", _P, _I, c_void_pp)
+_sig("sdr_pipe_u8_decimator", _P, _I, c_void_pp)
 lib.sdr_pipe_last_kernel.restype = C.c_char_p
 lib.sdr_pipe_last_kernel.argtypes = [C.c_void_p]
 _sig("sdr_pipe_convert_u8", _P, c_void_pp)
@@ -171,6 +172,7 @@ _sig("sdr_shard_plan", _LL, _I, _I, _I, _I, C.POINTER(ShardPlan))
 _sig("sdr_comm_unique_id", _P)
 _sig("sdr_comm_create", _P, _P, _I, _I, c_void_pp)
 _sig("sdr_comm_destroy", _P)
+_sig("sdr_comm_barrier", _P)
 _sig("sdr_comm_share_chunks", _P, _P)
 _sig("sdr_comm_peer_halo_active", _P, _P)
 _sig("sdr_decimate_sharded", _P, _P, C.POINTER(ShardPlan), _P, _P)
@@ -178,6 +180,13 @@ _sig("sdr_synth_noise", _P, _P, _LL, _LL, C.c_uint32)
 _sig("sdr_synth_bytes", _P, _P, _LL, _LL, C.c_uint32)
 _sig("sdr_flush_l2", _P)
 _sig("sdr_checksum32", _P, _P, _LL, _LL, C.POINTER(C.c_uint64))
+
+
+def check_group(ret):
+    """resampleCuda*: the reference's return convention (next group), negative = -(SDR_E*)"""
+    if ret < 0:
+        raise SdrError(-ret, lib.sdr_last_error().decode("utf-8", "replace"))
+    return ret
 
 
 def check(status):

@@ -91,8 +91,12 @@ Ctx *default_ctx(int *status);   // per-thread context behind the reference-sign
 // complex data, real taps, decimate by D.  Returns SDR_OK and sets *done to the number of leading outputs it
 // produced (a multiple of its tile; 0 when the shape / alignment has no tuned kernel); the caller finishes the rest
 // with launch_fir_generic.  *name receives a static string naming the instantiation.
-int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_in, long long n_in, float *d_out,
-                      long long num, long long *done, const char **name);
+// x = seg.a ++ seg.b.  When both sources and their boundary are 16-byte aligned the kernel covers ALL `num` outputs
+// (windows straddling the two segments and the ragged last tile included): *done == num.
+int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, Seg2 seg, float *d_out, long long num, long long *done,
+                      const char **name);
+// opt a kernel in to `smem_bytes` of dynamic shared memory, once per (kernel, device)
+int ring_attr(Ctx *c, const void *kernel, int smem_bytes);
 
 // real data, stride-1 FIR (kernels_real.cu); same contract as launch_dec_c_fast
 int launch_fir_r_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_in, long long n_in, float *d_out,
@@ -105,5 +109,9 @@ int launch_res_r_fast(Ctx *c, int L, int M, int n_taps, const float *d_plain_tap
 int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
                     float *d_out, long long num, float2 *d_bnd, long long bnd_capacity_subtiles, const float2 *d_carry,
                     float2 *d_carry_out, long long *done, const char **name);
+
+// fused u8 convert + decimate (complex outputs), same kernel without the discriminator
+int launch_dec_u8(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
+                  float *d_out, long long num, long long *done, const char **name);
 
 }  // namespace sdr

@@ -7,6 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace sdr {
 
@@ -60,6 +63,16 @@ int Ctx::ensure_dc_scratch(size_t bytes) {
     const size_t before = d_dc_scratch_bytes;
     SDR_TRY(grow(&d_dc_scratch, &d_dc_scratch_bytes, bytes, false));
     if (d_dc_scratch_bytes != before) dc_scratch_regrown = true;   // fresh block: the counters in its head are garbage
+    return SDR_OK;
+}
+
+int ring_attr(Ctx *c, const void *kernel, int smem_bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void *, int>> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    if (seen.count({kernel, c->device})) return SDR_OK;
+    SDR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    seen.insert({kernel, c->device});
     return SDR_OK;
 }
 

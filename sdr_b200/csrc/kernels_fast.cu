@@ -42,7 +42,8 @@ struct RingCfg {
 
 template <int T, int D, int R>
 __global__ void __launch_bounds__(256, 1)
-k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const float *__restrict__ taps, long long n_sub) {
+k_dec_c_ring(const float2 *__restrict__ in, long long a_bytes, const float2 *__restrict__ in_b, long long total_bytes,
+             float2 *__restrict__ out, long long num, const float *__restrict__ taps, long long n_sub) {
     typedef RingCfg<T, D, R> C;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,14 +68,61 @@ k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const floa
     __syncthreads();
 
     const unsigned char *gin = reinterpret_cast<const unsigned char *>(in);
+    // The stream is `in` (a_bytes bytes) followed by `in_b` (up to total_bytes; the right neighbour's chunk on a sharded
+    // pass, or nothing); everything beyond total_bytes reads as zero.  A fill that lies wholly inside `in` -- all of them
+    // except the last one or two of the last CTA -- takes the fast path: one 512-byte bulk copy per lane.
+    constexpr long long SUB_BYTES = (long long)C::SUB_OUT * C::BLK_BYTES;
+    const long long cta_bytes = a_bytes - s0 * SUB_BYTES;
+    const int fast_full = (int)(cta_bytes <= 0 ? 0 : (cta_bytes / SUB_BYTES > cnt ? cnt : cta_bytes / SUB_BYTES));
+    const bool halo_fast = cta_bytes >= cnt * SUB_BYTES + C::HALO_SEGS * C::SEG_BYTES;
+    auto issue_fill_edge = [&](int u) {
+        const int slot = u % C::NS;
+        const int nseg = (u == cnt) ? C::HALO_SEGS : 32;
+        const long long start = (s0 + u) * SUB_BYTES;
+        const uint32_t bar = bar_full + 8 * slot;
+        const long long ls = start + lane * C::SEG_BYTES;                       // stream offset of this lane's segment
+        long long v = total_bytes - ls;
+        const int valid = lane < nseg ? (int)(v < 0 ? 0 : (v > C::SEG_BYTES ? C::SEG_BYTES : v)) : 0;
+        const bool mirror = slot == 0 && lane < C::HALO_SEGS;
+        const uint32_t dst = ring + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE;
+        const uint32_t dst_m = ring + C::NS * C::SLOT_BYTES + lane * C::SEG_STRIDE;
+        if (lane < nseg)
+            for (int o = valid; o < C::SEG_BYTES; o += 16) {                    // what the stream does not hold reads as zero
+                asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst + o), "r"(0) : "memory");
+                if (mirror) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst_m + o), "r"(0) : "memory");
+            }
+        __syncwarp();
+        if (lane == 0) {
+            long long t = total_bytes - start;
+            long long tx = t < 0 ? 0 : (t > nseg * C::SEG_BYTES ? nseg * C::SEG_BYTES : t);
+            if (slot == 0) tx += t < 0 ? 0 : (t > C::HALO_SEGS * C::SEG_BYTES ? C::HALO_SEGS * C::SEG_BYTES : t);
+            mbar_expect_tx(bar, (uint32_t)tx);
+        }
+        __syncwarp();
+        if (valid > 0) {
+            long long va = a_bytes - ls;
+            const int from_a = (int)(va < 0 ? 0 : (va > valid ? valid : va));
+            const unsigned char *src_b = reinterpret_cast<const unsigned char *>(in_b) + (ls + from_a - a_bytes);
+            if (from_a > 0) {
+                bulk_g2s(dst, gin + ls, from_a, bar);
+                if (mirror) bulk_g2s(dst_m, gin + ls, from_a, bar);
+            }
+            if (valid > from_a) {
+                bulk_g2s(dst + from_a, src_b, valid - from_a, bar);
+                if (mirror) bulk_g2s(dst_m + from_a, src_b, valid - from_a, bar);
+            }
+        }
+        if (lane == 0) gen_publish(gen_armed + 4 * slot, u / C::NS + 1);
+    };
     auto issue_fill = [&](int u) {
+        if (!(u < fast_full || (u == cnt && halo_fast))) { issue_fill_edge(u); return; }
         int slot = u % C::NS;
         int nseg = (u == cnt) ? C::HALO_SEGS : 32;
         uint32_t bytes = nseg * C::SEG_BYTES + (slot == 0 ? C::HALO_SEGS * C::SEG_BYTES : 0);
         uint32_t bar = bar_full + 8 * slot;
         if (lane == 0) mbar_expect_tx(bar, bytes);
         __syncwarp();
-        const unsigned char *src = gin + (s0 + u) * (long long)(C::SUB_OUT * C::BLK_BYTES) + lane * C::SEG_BYTES;
+        const unsigned char *src = gin + (s0 + u) * SUB_BYTES + lane * C::SEG_BYTES;
         if (lane < nseg) bulk_g2s(ring + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE, src, C::SEG_BYTES, bar);
         if (slot == 0 && lane < C::HALO_SEGS)
             bulk_g2s(ring + C::NS * C::SLOT_BYTES + lane * C::SEG_STRIDE, src, C::SEG_BYTES, bar);
@@ -114,8 +162,13 @@ k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const floa
                 }
             }
         }
-        float2 *os = out + (s0 + u) * (long long)C::SUB_OUT + lane * R;
-        if (vec_store) {
+        const long long m0 = (s0 + u) * (long long)C::SUB_OUT + lane * R;
+        float2 *os = out + m0;
+        if (m0 + R > num) {   // ragged last sub-tile of the stream
+            u64 *o = reinterpret_cast<u64 *>(os);
+#pragma unroll
+            for (int r = 0; r < R; r++) if (m0 + r < num) o[r] = acc[r];
+        } else if (vec_store) {
             ulonglong2 *o = reinterpret_cast<ulonglong2 *>(os);
 #pragma unroll
             for (int r = 0; r < R; r += 2) o[r / 2] = make_ulonglong2(acc[r], acc[r + 1]);
@@ -139,39 +192,55 @@ k_dec_c_ring(const float2 *__restrict__ in, float2 *__restrict__ out, const floa
 }
 
 template <int T, int D, int R>
-static int launch_ring(Ctx *c, const float *d_taps, const float *d_in, long long n_in, float *d_out, long long num,
-                       long long *done) {
+static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, float *d_out, long long num, long long *done) {
     typedef RingCfg<T, D, R> C;
     static_assert(R % 2 == 0, "outputs per lane are stored in 16-byte pairs");
-    long long blocks_avail = n_in / D;
-    long long by_in = (blocks_avail - C::HALO_SEGS * R) / C::SUB_OUT;   // a pass also loads HALO_SEGS whole segments
-    long long n_sub = num / C::SUB_OUT;
-    if (by_in < n_sub) n_sub = by_in;
-    if (n_sub <= 0) { *done = 0; return SDR_OK; }
-    SDR_TRY(c->bind());
-    static thread_local int attr_dev = -1;
-    if (attr_dev != c->device) {
-        SDR_CUDA(cudaFuncSetAttribute(k_dec_c_ring<T, D, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        attr_dev = c->device;
+    const long long n_in = seg.na + seg.nb;
+    const long long needed = (num - 1) * D + T;                 // samples the `num` outputs read
+    const long long needed2 = (needed + 1) & ~1LL;              // bulk copies move whole 16-byte units (two samples)
+    const long long usable = n_in & ~1LL;
+    long long n_sub, a_bytes, total_bytes;
+    // COVERING mode: the kernel produces all `num` outputs, ragged last sub-tile and windows that run into the second
+    // segment included (its edge fills split a lane segment between the two sources and zero-fill what lies beyond).
+    // It needs both sources and the boundary between them on 16-byte boundaries.
+    const bool covering = num > 0 && needed2 <= usable && (seg.na % 2) == 0 && (seg.nb == 0 || (((uintptr_t)seg.b) & 15) == 0);
+    if (covering) {
+        n_sub = (num + C::SUB_OUT - 1) / C::SUB_OUT;
+        a_bytes = seg.na * 8;
+        total_bytes = usable * 8;
+        if (total_bytes < a_bytes) a_bytes = total_bytes;
+        *done = num;
+    } else {
+        // interior only: the sub-tiles whose whole window (halo segments included) is resident in the first segment
+        long long blocks_avail = seg.na / D;
+        long long by_in = (blocks_avail - C::HALO_SEGS * R) / C::SUB_OUT;
+        n_sub = num / C::SUB_OUT;
+        if (by_in < n_sub) n_sub = by_in;
+        if (n_sub <= 0) { *done = 0; return SDR_OK; }
+        a_bytes = total_bytes = (seg.na * 8) & ~15LL;
+        *done = n_sub * C::SUB_OUT;
     }
+    SDR_TRY(c->bind());
+    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_c_ring<T, D, R>), C::SMEM_BYTES));
     int sms = c->sm_count - c->reserve_sms;
     if (sms < 1) sms = 1;
     int grid = (int)(n_sub < sms ? n_sub : sms);
-    k_dec_c_ring<T, D, R><<<grid, 256, C::SMEM_BYTES, c->s()>>>((const float2 *)d_in, (float2 *)d_out, d_taps, n_sub);
+    const long long num_mask = covering ? num : n_sub * C::SUB_OUT;
+    k_dec_c_ring<T, D, R><<<grid, 256, C::SMEM_BYTES, c->s()>>>((const float2 *)seg.a, a_bytes, (const float2 *)seg.b, total_bytes,
+                                                                  (float2 *)d_out, num_mask, d_taps, n_sub);
     c->launches++;
     SDR_CUDA(cudaGetLastError());
-    *done = n_sub * C::SUB_OUT;
     return SDR_OK;
 }
 
-int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_in, long long n_in, float *d_out,
-                      long long num, long long *done, const char **name) {
+int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, Seg2 seg, float *d_out, long long num, long long *done,
+                      const char **name) {
     *done = 0;
     *name = "fir_direct";
-    if ((((uintptr_t)d_in) & 15) != 0) return SDR_OK;   // TMA bulk copies need a 16-byte aligned source; any output alignment
+    if ((((uintptr_t)seg.a) & 15) != 0) return SDR_OK;   // TMA bulk copies need a 16-byte aligned source; any output alignment
     if (T == 128 && D == 8) {
         *name = "dec_c_ring<128,8,8>";
-        return launch_ring<128, 8, 8>(c, d_taps, d_in, n_in, d_out, num, done);
+        return launch_ring<128, 8, 8>(c, d_taps, seg, d_out, num, done);
     }
     return SDR_OK;
 }

@@ -70,7 +70,9 @@ __device__ __forceinline__ float2 unpack2f(u64 v) {
 // SYM: the taps are symmetric (c[k] = c[T-1-k], the usual linear-phase design): only T/2 of them are kept in registers,
 // which halves the register footprint and lets 16 warps (instead of 8) share the SM -- the epilogue is latency bound,
 // so the extra warps are what fills the FP32 pipe.  Same tap values in the same order: bit-identical results.
-template <int T, int D, int R, int NW, bool SYM>
+// DEMOD = false: the same kernel without the discriminator -- `P.map interleavedIQUnsignedByteToFloat >-> firDecimator`
+// (fm.hs:34-36) alone: `out` then receives the decimated COMPLEX samples (8 B each), bnd / carry_out are unused.
+template <int T, int D, int R, int NW, bool SYM, bool DEMOD = true>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_fm_front_ring(const uint8_t *__restrict__ in, long long n_chunks, float *__restrict__ out, long long num,
                 float2 *__restrict__ bnd, float2 *__restrict__ carry_out, const float *__restrict__ taps, long long n_sub) {
@@ -166,6 +168,19 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long n_chunks, float *__res
             issue_fill(u + C::NS);
         }
 
+        const long long m0 = (s0 + u) * (long long)C::SUB_OUT + lane * R;   // this lane's first output index
+        if (!DEMOD) {
+            u64 *os = reinterpret_cast<u64 *>(out) + m0;
+            if (vec_store && m0 + R <= num) {
+                ulonglong2 *o = reinterpret_cast<ulonglong2 *>(os);
+#pragma unroll
+                for (int r = 0; r < R; r += 2) o[r / 2] = make_ulonglong2(acc[r], acc[r + 1]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) if (m0 + r < num) os[r] = acc[r];
+            }
+            continue;
+        }
         // epilogue: FM discriminator
         float2 y[R];
 #pragma unroll
@@ -177,7 +192,6 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long n_chunks, float *__res
         ph[0] = fm_phase(y[0], prev);   // lane 0's value is meaningless here: patched by k_fm_front_fixup
 #pragma unroll
         for (int r = 1; r < R; r++) ph[r] = fm_phase(y[r], y[r - 1]);
-        const long long m0 = (s0 + u) * (long long)C::SUB_OUT + lane * R;   // this lane's first output index
         float *os = out + m0;
         if (vec_store && m0 + R <= num) {
             float4 *o = reinterpret_cast<float4 *>(os);
@@ -220,20 +234,12 @@ int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, c
     int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
     if (symmetric) {
         typedef FmCfg<128, 8, 8, 16> C;
-        static thread_local int attr_dev = -1;
-        if (attr_dev != c->device) {
-            SDR_CUDA(cudaFuncSetAttribute(k_fm_front_ring<128, 8, 8, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-            attr_dev = c->device;
-        }
+        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<128, 8, 8, 16, true>), C::SMEM_BYTES));
         k_fm_front_ring<128, 8, 8, 16, true><<<grid, 512, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
         *name = "fm_front_ring<128,8,8,sym,16w>";
     } else {
         typedef FmCfg<128, 8, 8, 8> C;
-        static thread_local int attr_dev = -1;
-        if (attr_dev != c->device) {
-            SDR_CUDA(cudaFuncSetAttribute(k_fm_front_ring<128, 8, 8, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-            attr_dev = c->device;
-        }
+        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<128, 8, 8, 8, false>), C::SMEM_BYTES));
         k_fm_front_ring<128, 8, 8, 8, false><<<grid, 256, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
         *name = "fm_front_ring<128,8,8>";
     }
@@ -242,6 +248,35 @@ int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, c
     long long fg = (n_sub + 255) / 256;
     if (fg > 4LL * c->sm_count) fg = 4LL * c->sm_count;
     k_fm_front_fixup<<<(int)fg, 256, 0, c->s()>>>(d_out, d_bnd, d_carry, n_sub, 256);
+    c->launches++;
+    SDR_CUDA(cudaGetLastError());
+    *done = num;
+    return SDR_OK;
+}
+
+// Fused convert + decimate (no demodulation) of outputs [0, num) of a byte stream holding n_samples IQ pairs: complex
+// outputs.  *done = num when the shape has a tuned kernel, else 0 (the caller runs the two stages one after the other).
+int launch_dec_u8(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
+                  float *d_out, long long num, long long *done, const char **name) {
+    *done = 0;
+    *name = "unfused";
+    if (T != 128 || D != 8 || num <= 0) return SDR_OK;
+    if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 7) != 0) return SDR_OK;
+    if ((num - 1) * D + T > n_samples) return set_error(SDR_EINVAL, "launch_dec_u8: %lld outputs need more than %lld samples", num, n_samples);
+    const long long n_sub = (num + 255) / 256;
+    SDR_TRY(c->bind());
+    int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
+    if (symmetric) {
+        typedef FmCfg<128, 8, 8, 16> C;
+        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<128, 8, 8, 16, true, false>), C::SMEM_BYTES));
+        k_fm_front_ring<128, 8, 8, 16, true, false><<<grid, 512, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, nullptr, nullptr, d_taps, n_sub);
+        *name = "dec_u8_ring<128,8,8,sym,16w>";
+    } else {
+        typedef FmCfg<128, 8, 8, 8> C;
+        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<128, 8, 8, 8, false, false>), C::SMEM_BYTES));
+        k_fm_front_ring<128, 8, 8, 8, false, false><<<grid, 256, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, nullptr, nullptr, d_taps, n_sub);
+        *name = "dec_u8_ring<128,8,8>";
+    }
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     *done = num;

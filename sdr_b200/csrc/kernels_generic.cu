@@ -166,12 +166,8 @@ static int launch_direct(Ctx *c, bool cplx, OutMap m, int T, const float *d_taps
     size_t smem = (((size_t)n_rows * row_floats * 4 + 15) / 16) * 16 + (size_t)span * (cplx ? 8 : 4);
     static const bool no_tile = getenv("SDR_B200_NOTILE") != nullptr;   // debugging aid: force the direct kernel
     if (smem <= 200 * 1024 && !no_tile) {
-        static thread_local int attr_dev = -1;
-        if (attr_dev != c->device) {
-            SDR_CUDA(cudaFuncSetAttribute(k_fir_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            SDR_CUDA(cudaFuncSetAttribute(k_fir_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_dev = c->device;
-        }
+        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fir_tile<true>), 200 * 1024));
+        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fir_tile<false>), 200 * 1024));
         long long tiles = (num + TILE_OUT - 1) / TILE_OUT;
         long long cap = (long long)c->sm_count * (smem > 48 * 1024 ? 1 : 8);
         int grid = (int)(tiles < cap ? tiles : cap);

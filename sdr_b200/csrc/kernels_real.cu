@@ -154,11 +154,7 @@ static int launch_fir_r(Ctx *c, const float *d_taps, const float *d_in, long lon
     if (by_in < n_slots) n_slots = by_in;
     if (n_slots <= 0) { *done = 0; return SDR_OK; }
     SDR_TRY(c->bind());
-    static thread_local int attr_dev = -1;
-    if (attr_dev != c->device) {
-        SDR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::Ring::SMEM_BYTES));
-        attr_dev = c->device;
-    }
+    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(kernel), C::Ring::SMEM_BYTES));
     int sms = c->sm_count - c->reserve_sms;
     if (sms < 1) sms = 1;
     int grid = (int)(n_slots < sms ? n_slots : sms);
@@ -287,11 +283,7 @@ static int launch_res_r(Ctx *c, const float *d_taps, const float *d_in, long lon
     if (by_in < n_slots) n_slots = by_in;
     if (n_slots <= 0) { *done = 0; return SDR_OK; }
     SDR_TRY(c->bind());
-    static thread_local int attr_dev = -1;
-    if (attr_dev != c->device) {
-        SDR_CUDA(cudaFuncSetAttribute(k_res_r_ring<L, M, T, CY, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::Ring::SMEM_BYTES));
-        attr_dev = c->device;
-    }
+    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_res_r_ring<L, M, T, CY, S>), C::Ring::SMEM_BYTES));
     int sms = c->sm_count - c->reserve_sms;
     if (sms < 1) sms = 1;
     int grid = (int)(n_slots < sms ? n_slots : sms);

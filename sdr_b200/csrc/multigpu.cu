@@ -26,6 +26,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -50,10 +51,11 @@ static int nccl_api(NcclApi **out) {
             SDR_SYM(Send, "ncclSend");
             SDR_SYM(Recv, "ncclRecv");
             SDR_SYM(AllGather, "ncclAllGather");
+            SDR_SYM(AllReduce, "ncclAllReduce");
             SDR_SYM(GetErrorString, "ncclGetErrorString");
 #undef SDR_SYM
             if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send &&
-                api.Recv && api.GetErrorString)
+                api.Recv && api.AllGather && api.AllReduce && api.GetErrorString)
                 state = 1;
         }
     }
@@ -84,6 +86,7 @@ struct sdr_comm {
     const void *my_base = nullptr;   // the allocation this rank registered
     void *peer_base = nullptr;       // rank+1's allocation as seen from here (nullptr: NCCL transport)
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
+    int *d_token = nullptr;          // sdr_comm_barrier's all-reduce operand
 };
 
 extern "C" {
@@ -153,6 +156,7 @@ int sdr_comm_destroy(sdr_comm_t *c) {
     cudaStreamSynchronize(c->ctx->side);
     if (c->comm) c->api->CommDestroy(c->comm);
     if (c->d_halo) cudaFree(c->d_halo);
+    if (c->d_token) cudaFree(c->d_token);
     if (c->peer_base) cudaIpcCloseMemHandle(c->peer_base);
     if (c->ev_ready) cudaEventDestroy(c->ev_ready);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
@@ -194,6 +198,19 @@ int sdr_comm_share_chunks(sdr_comm_t *c, const void *d_chunk_base) {
     return SDR_OK;
 }
 
+// In-stream rendezvous: a 4-byte ncclAllReduce on the ctx stream.  Work enqueued behind it starts on every rank within
+// the collective's completion skew (microseconds) -- unlike a host-side barrier, which leaves each rank's launch latency
+// and host jitter inside whatever is timed next.
+int sdr_comm_barrier(sdr_comm_t *c) {
+    if (!c) return set_error(SDR_EINVAL, "sdr_comm_barrier: null communicator");
+    Ctx *ctx = c->ctx;
+    SDR_TRY(ctx->bind());
+    if (c->world == 1) return SDR_OK;
+    if (!c->d_token) { SDR_CUDA(cudaMalloc(&c->d_token, 8)); SDR_CUDA(cudaMemsetAsync(c->d_token, 0, 8, ctx->stream)); }
+    SDR_NCCL(c->api, c->api->AllReduce(c->d_token, c->d_token + 1, 1, ncclInt, ncclSum, c->comm, ctx->stream));
+    return SDR_OK;
+}
+
 // 1 when sdr_decimate_sharded on this d_in would use the peer-memory transport
 int sdr_comm_peer_halo_active(const sdr_comm_t *c, const void *d_in) {
     return c && c->my_base && c->my_base == d_in ? 1 : 0;
@@ -214,27 +231,24 @@ int sdr_decimate_sharded(sdr_decimator_t *d, sdr_comm_t *c, const sdr_shard_t *p
     const long long local0 = plan->out_begin * plan->factor - plan->in_begin;
     bool exchange = false;
     const bool peer = plan->world > 1 && c->my_base && c->my_base == d_in;
+    // the windows of this rank's last outputs run `halo` samples into the right neighbour's chunk: that chunk must hold
+    // them (evaluated identically on every rank from the plan alone, so all ranks fail together -- none is left blocked
+    // in a collective)
+    for (int q = 0; q + 1 < plan->world; q++) {
+        sdr_shard_t a, b;
+        SDR_TRY(sdr_shard_plan(plan->n_samples, plan->taps, plan->factor, plan->world, q, &a));
+        SDR_TRY(sdr_shard_plan(plan->n_samples, plan->taps, plan->factor, plan->world, q + 1, &b));
+        if (a.halo > b.in_count)
+            return set_error(SDR_EPRECOND, "sdr_decimate_sharded: rank %d's chunk of %lld samples is shorter than the %lld-sample halo of rank %d",
+                             q + 1, b.in_count, a.halo, q);
+    }
     if (peer) {
-        // halo read in place from the neighbour's HBM: tuned kernel over the resident sub-tiles on the main stream (all
-        // SMs), ragged end + boundary windows in one generic launch on the side stream with seg.b = the neighbour's chunk
+        // Halo read in place from the neighbour's HBM over NVLink, INSIDE the ring kernel: its edge fills take the last
+        // T-D samples of the boundary windows from the second source pointer (TMA bulk copies of peer memory), so a pass
+        // is ONE launch -- no NCCL kernel, no rendezvous, no side stream, no SMs set aside.
         if (plan->halo > 0 && !c->peer_base) return set_error(SDR_EPRECOND, "sdr_decimate_sharded: no mapped right neighbour");
-        long long done = 0;
-        const char *kernel = r.last_kernel;
-        SDR_CUDA(cudaEventRecord(c->ev_ready, ctx->stream));
-        SDR_TRY(r.run_tuned(d_in, plan->in_count, local0, d_out, plan->out_interior, &done));
-        if (done > 0) kernel = r.last_kernel;
-        if (plan->out_count > done) {
-            SDR_CUDA(cudaStreamWaitEvent(ctx->side, c->ev_ready, 0));
-            Seg2 seg = {d_in, plan->in_count, c->peer_base, plan->halo};
-            ctx->override_st = ctx->side;
-            int rc = r.run(seg, local0 + done * plan->factor, (char *)d_out + (size_t)done * eb, plan->out_count - done, false);
-            ctx->override_st = nullptr;
-            SDR_TRY(rc);
-            SDR_CUDA(cudaEventRecord(c->ev_halo, ctx->side));
-            SDR_CUDA(cudaStreamWaitEvent(ctx->stream, c->ev_halo, 0));
-        }
-        r.last_kernel = kernel;
-        return SDR_OK;
+        Seg2 seg = {d_in, plan->in_count, plan->halo > 0 ? c->peer_base : nullptr, plan->halo};
+        return r.run(seg, local0, d_out, plan->out_count, false);
     }
     if (plan->world > 1) {
         // what my left neighbour needs from the head of my chunk
@@ -242,9 +256,6 @@ int sdr_decimate_sharded(sdr_decimator_t *d, sdr_comm_t *c, const sdr_shard_t *p
         long long send = 0;
         if (plan->rank > 0) { SDR_TRY(sdr_shard_plan(plan->n_samples, plan->taps, plan->factor, plan->world, plan->rank - 1, &left));
                               send = left.halo; }
-        if (send > plan->in_count)
-            return set_error(SDR_EPRECOND, "sdr_decimate_sharded: chunk of %lld samples is shorter than the %lld-sample halo",
-                             plan->in_count, send);
         long long recv = plan->halo;
         if (send || recv) {
             exchange = true;

@@ -100,7 +100,7 @@ static void trace_dump() {
     trace_log().clear();
 }
 
-enum { P_FILTER, P_DECIM, P_RESAMP, P_FMDEMOD, P_CONVERT, P_SCALE, P_FMFRONT, P_DCBLOCK };
+enum { P_FILTER, P_DECIM, P_RESAMP, P_FMDEMOD, P_CONVERT, P_SCALE, P_FMFRONT, P_DCBLOCK, P_U8DECIM };
 
 }  // namespace sdr
 
@@ -142,7 +142,8 @@ struct sdr_pipe {
 
 namespace sdr {
 
-static bool is_fir_kind(int k) { return k == P_FILTER || k == P_DECIM || k == P_RESAMP || k == P_FMFRONT; }
+static bool is_fir_kind(int k) { return k == P_FILTER || k == P_DECIM || k == P_RESAMP || k == P_FMFRONT || k == P_U8DECIM; }
+static bool is_byte_fed(int k) { return k == P_FMFRONT || k == P_U8DECIM; }
 
 static int fifo_writable(sdr_pipe *p) {
     if (p->d2h_outstanding) { SDR_CUDA(cudaStreamWaitEvent(p->ctx->stream, p->ev_out_done, 0)); p->d2h_outstanding = false; }
@@ -255,6 +256,36 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     return SDR_OK;
 }
 
+// P.map convert >-> firDecimator as one stage (complex outputs): the fused kernel without the discriminator; shapes
+// without a tuned kernel convert into scratch and run the decimator record on it.
+static int process_u8_decim(sdr_pipe *p, long long fifo_have, long long batch) {
+    FirRec &f = *p->fir;
+    const long long have = (long long)(p->in.size() / 2);   // IQ pairs resident
+    long long count = (have >= f.T) ? (have - f.T) / f.D + 1 : 0;
+    if (!(count > 0 && fifo_have + count >= p->block_out && fifo_have + count >= batch)) return SDR_OK;
+    SDR_TRY(flush_pending(p));
+    TraceScope tr("u8_decimator", p->ctx, count);
+    SDR_TRY(fifo_writable(p));
+    SDR_TRY(p->fifo.reserve((size_t)count * 8));
+    float *out = (float *)(p->fifo.p + p->fifo.wr);
+    long long done = 0;
+    const char *name = nullptr;
+    SDR_TRY(launch_dec_u8(p->ctx, f.T, f.D, f.d_taps, f.symmetric, (const uint8_t *)(p->in.p + p->in.rd), have, out, count, &done, &name));
+    p->last_kernel = name;
+    if (done < count) {
+        const long long n_s = (count - 1) * f.D + f.T;
+        p->scratch_x.rd = p->scratch_x.wr = 0;
+        SDR_TRY(p->scratch_x.reserve((size_t)n_s * 8 + 256));
+        SDR_TRY(launch_convert_u8(p->ctx, (const uint8_t *)(p->in.p + p->in.rd), (float *)p->scratch_x.p, 2 * n_s));
+        Seg2 seg = {p->scratch_x.p, n_s, nullptr, 0};
+        SDR_TRY(f.run(seg, 0, out, count, false));
+    }
+    p->fifo.wr += (size_t)count * 8;
+    p->in.rd += (size_t)(count * f.D) * 2;
+    if (p->in.size() <= (1u << 16) && p->in.rd > p->in.cap / 4) SDR_TRY(p->in.realign(0));
+    return SDR_OK;
+}
+
 // run whatever the stream now allows (FIR kinds); data already appended to p->in
 static int process_fir(sdr_pipe *p, bool force = false) {
     long long have = (long long)(p->in.size() / p->in_eb);
@@ -291,6 +322,7 @@ static int process_fir(sdr_pipe *p, bool force = false) {
         return SDR_OK;
     }
     if (p->kind == P_FMFRONT) return process_fm_front(p, fifo_have, batch);
+    if (p->kind == P_U8DECIM) return process_u8_decim(p, fifo_have, batch);
     FirRec &f = *p->fir;
     long long count = (have >= f.T) ? (have - f.T) / f.D + 1 : 0;
     if (count > 0 && fifo_have + count >= p->block_out && (fifo_have + count >= batch)) {
@@ -343,8 +375,8 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, lon
     if (is_fir_kind(p->kind)) {
         // the reference asserts every awaited vector holds at least numCoeffs samples (Filter.hs:544,586,691)
         long long need = (p->kind == P_RESAMP) ? (p->res->T + p->res->L - 1) / p->res->L : p->fir->T;
-        if (p->kind == P_FMFRONT) {
-            if (n & 1) return set_error(SDR_EINVAL, "FM front end: odd byte count %lld (interleaved I/Q pairs expected)", n);
+        if (is_byte_fed(p->kind)) {
+            if (n & 1) return set_error(SDR_EINVAL, "u8 IQ stage: odd byte count %lld (interleaved I/Q pairs expected)", n);
             need *= 2;
         }
         if (n < need) return set_error(SDR_EPRECOND, "%s 1: input vector of %lld elements is shorter than numCoeffs (%lld)",
@@ -431,6 +463,15 @@ int sdr_pipe_fm_frontend(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **ou
     p->bnd.c = p->scratch_x.c = p->scratch_y.c = p->ctx;
     SDR_CUDA(cudaMalloc(&p->d_last, 16));
     SDR_CUDA(cudaMemsetAsync(p->d_last, 0, 16, p->ctx->stream));
+    return SDR_OK;
+}
+int sdr_pipe_u8_decimator(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **out) {
+    if (!d || block_size_out <= 0) return set_error(SDR_EINVAL, "sdr_pipe_u8_decimator: bad argument");
+    if (!d->r.cplx) return set_error(SDR_EINVAL, "sdr_pipe_u8_decimator: the decimator must be a complex-data one (fastDecimatorC)");
+    sdr_pipe *p;
+    SDR_TRY(new_pipe(d->r.ctx, P_U8DECIM, out, &p));
+    p->fir = &d->r; p->in_eb = 1; p->out_eb = 8; p->block_out = block_size_out; p->assert_name = "decimate";
+    p->scratch_x.c = p->ctx;
     return SDR_OK;
 }
 const char *sdr_pipe_last_kernel(const sdr_pipe_t *p) { return p ? p->last_kernel : "none"; }
@@ -542,7 +583,7 @@ int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs) {
         // size both buffers for the batch once, instead of growing by doubling while the stream runs
         SDR_TRY(p->ctx->bind());
         long long in_per_out = (p->kind == P_RESAMP) ? (p->res->M + p->res->L - 1) / p->res->L
-                             : (p->kind == P_FMFRONT) ? 2 * p->fir->D : p->fir->D;
+                             : is_byte_fed(p->kind) ? 2 * p->fir->D : p->fir->D;
         long long taps = (p->kind == P_RESAMP) ? p->res->T : p->fir->T;
         SDR_TRY(p->in.reserve((size_t)(2 * (min_outputs + p->block_out) * in_per_out + taps) * p->in_eb));
         SDR_TRY(p->fifo.reserve((size_t)(2 * (min_outputs + p->block_out)) * p->out_eb));

@@ -94,7 +94,7 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
         // on the side stream concurrently with the tuned kernel (fork before, join after).
         if (can_fork) SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
         const char *name = nullptr;
-        if (cplx) SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, (const float *)seg.a, seg.na, (float *)d_out, num, &done, &name));
+        if (cplx) SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, seg, (float *)d_out, num, &done, &name));
         else      SDR_TRY(launch_fir_r_fast(ctx, T, D, d_taps, (const float *)seg.a, seg.na, (float *)d_out, num, &done, &name));
         if (done > 0) last_kernel = name;
     }
@@ -120,8 +120,8 @@ int FirRec::run_tuned(const void *d_in, long long n_in, long long first, void *d
     *done = 0;
     if (num <= 0 || !cplx || arith != SDR_ARITH_FAST) return SDR_OK;
     const char *name = nullptr;
-    SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, (const float *)((const char *)d_in + first * 8), n_in - first, (float *)d_out, num,
-                              done, &name));
+    Seg2 seg = {(const char *)d_in + first * 8, n_in - first, nullptr, 0};
+    SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, seg, (float *)d_out, num, done, &name));
     if (*done > 0) last_kernel = name;
     return SDR_OK;
 }
@@ -408,15 +408,22 @@ int sdr_exact_decimate(int variant, int is_complex, int num, int factor, int num
     return oneshot_fir("sdr_exact_decimate", kind, is_complex != 0, num, factor, numCoeffs, coeffs, inBuf, outBuf, variant);
 }
 
-int resampleCudaRR(int buf_size, int num_coeffs, int starting_group, int num_groups, const int *increments,
-                   const float *const *coeffs, const float *in_buf, float *out_buf, int *next_group) {
-    return oneshot_resample("resampleCudaRR", false, buf_size, num_coeffs, starting_group, num_groups, increments, coeffs,
-                            nullptr, 0, in_buf, out_buf, next_group, -1);
+// resample2RR / resampleSSERR / resampleAVXRR and the RC forms (resample.c:34-142): the reference's exact signature --
+// 8 arguments, the RETURN VALUE is the next group (what FilterInternal.mkResampler binds, :335-342, 358-362).  A
+// failure returns -(status) < 0 with the message in sdr_last_error(); the reference's C cannot fail (void of errors).
+int resampleCudaRR(int buf_size, int num_coeffs, int starting_group, int num_groups, int *increments, float **coeffs,
+                   float *in_buf, float *out_buf) {
+    int next = 0;
+    int rc = oneshot_resample("resampleCudaRR", false, buf_size, num_coeffs, starting_group, num_groups, increments, coeffs,
+                              nullptr, 0, in_buf, out_buf, &next, -1);
+    return rc == SDR_OK ? next : -rc;
 }
-int resampleCudaRC(int buf_size, int num_coeffs, int starting_group, int num_groups, const int *increments,
-                   const float *const *coeffs, const float *in_buf, float *out_buf, int *next_group) {
-    return oneshot_resample("resampleCudaRC", true, buf_size, num_coeffs, starting_group, num_groups, increments, coeffs,
-                            nullptr, 0, in_buf, out_buf, next_group, -1);
+int resampleCudaRC(int buf_size, int num_coeffs, int starting_group, int num_groups, int *increments, float **coeffs,
+                   float *in_buf, float *out_buf) {
+    int next = 0;
+    int rc = oneshot_resample("resampleCudaRC", true, buf_size, num_coeffs, starting_group, num_groups, increments, coeffs,
+                              nullptr, 0, in_buf, out_buf, &next, -1);
+    return rc == SDR_OK ? next : -rc;
 }
 int sdr_exact_resample(int variant, int is_complex, int buf_size, int num_coeffs, int starting_group, int num_groups,
                        const int *increments, const float *table, int row_stride, const float *in_buf, float *out_buf,

@@ -30,6 +30,10 @@ class Comm:
         """collective: map the right neighbour's chunk (CUDA IPC) so the halo is read in place over NVLink"""
         L.check(L.lib.sdr_comm_share_chunks(self.h, d_chunk_base))
 
+    def barrier(self):
+        """in-stream rendezvous (4-byte ncclAllReduce on the ctx stream); enqueue-only"""
+        L.check(L.lib.sdr_comm_barrier(self.h))
+
     def peer_halo_active(self, d_in) -> bool:
         return bool(L.lib.sdr_comm_peer_halo_active(self.h, d_in))
 

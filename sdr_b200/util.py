@@ -108,6 +108,14 @@ def pipeFmFrontEnd(decimator, blockSizeOut) -> NativePipe:
     return NativePipe(h, decimator.ctx, np.uint8, np.float32, owner=decimator)
 
 
+def pipeU8Decimator(decimator, blockSizeOut) -> NativePipe:
+    """P.map interleavedIQUnsignedByteToFloat >-> firDecimator decimator blockSizeOut  (fm.hs:34-36), fused: u8 IQ bytes
+    in, complex samples out"""
+    h = C.c_void_p()
+    L.check(L.lib.sdr_pipe_u8_decimator(decimator.handle, blockSizeOut, C.byref(h)))
+    return NativePipe(h, decimator.ctx, np.uint8, np.complex64, owner=decimator)
+
+
 def fmDemod(src: Iterable[np.ndarray], ctx=None) -> Iterator[np.ndarray]:
     """fmDemod :: Pipe (v (Complex a)) (v a) IO ()  (Demod.hs:38-46)"""
     pipe = pipeFmDemod(ctx)

@@ -47,9 +47,12 @@ def checksum32(words, first=0):
 
 
 def windowed_sinc_taps(n, cutoff, gain=1.0):
-    """Hamming-windowed sinc centred at (n-1)/2 (SDR.FilterDesign formulas, hs_sources/SDR/FilterDesign.hs:33-68,
-    generalised to even lengths), float64 -> float32; symmetric."""
-    k = np.arange(n, dtype=np.float64) - (n - 1) / 2.0
-    h = np.sinc(2 * cutoff * k) * 2 * cutoff
-    w = 0.54 - 0.46 * np.cos(2 * np.pi * np.arange(n) / (n - 1))
-    return (gain * h * w).astype(np.float32)
+    """the package's tap designer (sdr_b200/filterdesign.py), loaded by path so that CPU-only users of this module do not
+    need the native library"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "_sdr_b200_filterdesign", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sdr_b200", "filterdesign.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.windowed_sinc_taps(n, cutoff, gain)

@@ -187,11 +187,12 @@ def test_resample_fast_vs_reference(L, ref, cplx, interp, decim, T):
     xf = L.as_floats(x)
     out = np.zeros(num * (2 if cplx else 1), np.float32)
     inc = np.ascontiguousarray(increments, np.int32)
-    g = C.c_int()
     fn = L.lib.resampleCudaRC if cplx else L.lib.resampleCudaRR
-    L.check(fn(num, num_coeffs, 0, len(increments), L.ptr(inc), rows, L.ptr(xf), L.ptr(out), C.byref(g)))
+    # the reference's own signature: 8 arguments, returns the next group (resample.c:70-87)
+    g = L.check_group(fn(num, num_coeffs, 0, len(increments), L.ptr(inc), rows, L.ptr(xf), L.ptr(out)))
     got = out.view(np.complex64) if cplx else out
-    assert g.value == g_want
+    assert g == g_want
+    assert fn(num, num_coeffs, len(increments), len(increments), L.ptr(inc), rows, L.ptr(xf), L.ptr(out)) == -L.SDR_EINVAL
     close(got, want)
     close(got, op.flat_resample(x, taps, interp, decim, num).astype(got.dtype), rtol=2e-6)
 
@@ -727,3 +728,32 @@ def test_sharded_plan_single_rank_equals_stream(sdr, L, ctx):
     sdr.multigpu.decimate_sharded(d, None, plan, x.ptr, y.ptr)
     L.check(L.lib.sdr_decimate_stream(d.handle, x.ptr, n, y2.ptr, plan.out_count))
     assert ctx.checksum32(y, 2 * plan.out_count) == ctx.checksum32(y2, 2 * plan.out_count)
+
+
+@pytest.mark.parametrize("n_last,n_next,count", [
+    (2048 * 5, 120, 2048 * 5 // 8),              # a shard boundary: every window that STARTS in `last`, 120-sample halo
+    ((1 << 16) + 2, 1000, None),                 # boundary inside a lane segment, ragged last sub-tile
+    ((1 << 16) + 64 * 3, 128, None),             # boundary on a lane-segment edge
+    (4096, 4096, 300),                           # only the head of `next` is needed
+])
+def test_ring_kernel_covers_two_segments_and_ragged_end(sdr, L, ctx, ref, n_last, n_next, count):
+    """the headline ring kernel in COVERING mode (one launch, no generic tail): windows that straddle lastBuf ++ nextBuf
+    (what a sharded pass reads from its neighbour) and the ragged last sub-tile, against the reference AVX C"""
+    taps = synth.windowed_sinc_taps(128, 1 / 16)
+    d = sdr.cudaDecimatorC(8, taps, sizeMultiple=4)
+    if count is None:
+        count = (n_last + n_next - 128) // 8 + 1
+    xs = synth.noise_complex(n_last + n_next, first=12345)
+    a = ctx.to_device(xs[:n_last])
+    b = ctx.to_device(xs[n_last:])
+    y = ctx.alloc(8 * count + 64)
+    L.check(L.lib.sdr_memset_dev(ctx.h, y.ptr, 0xff, 8 * count + 64))
+    before = ctx.launches
+    L.check(L.lib.sdr_decimate_cross(d.handle, count, a.ptr, n_last, b.ptr, n_next, y.ptr, L.SDR_DEVICE))
+    assert d.last_kernel().startswith("dec_c_ring") and ctx.launches - before == 1, (d.last_kernel(), ctx.launches - before)
+    got = y.to_host(np.complex64, count + 8)
+    want = ref.decimate("decimateAVXRC", count, 8, np.repeat(taps, 2), xs)
+    close(got[:count], want)
+    assert np.all(got[count:].view(np.uint32) == 0xffffffff), "stores past the last output"
+    for buf in (a, b, y):
+        buf.free()

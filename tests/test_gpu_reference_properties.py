@@ -123,11 +123,10 @@ def test_prop_resamplers(L, ref, seed):
         names = ("resample2RC", "resampleAVXRC") if cplx else ("resample2RR", "resampleAVXRR")
         res = [(n, ref.resample(n, num, num_coeffs, start, increments, groups, x)) for n in names]
         out = np.zeros(num * (2 if cplx else 1), np.float32)
-        g = C.c_int()
         xf = L.as_floats(x)
-        L.check((L.lib.resampleCudaRC if cplx else L.lib.resampleCudaRR)(num, num_coeffs, start, len(increments), L.ptr(inc), rows,
-                                                                         L.ptr(xf), L.ptr(out), C.byref(g)))
-        assert all(g.value == r[1] for _, r in res)
+        g = L.check_group((L.lib.resampleCudaRC if cplx else L.lib.resampleCudaRR)(num, num_coeffs, start, len(increments), L.ptr(inc), rows,
+                                                                                   L.ptr(xf), L.ptr(out)))
+        assert all(g == r[1] for _, r in res)
         _agree([(n, r[0]) for n, r in res] + [("cuda", out.view(np.complex64) if cplx else out)], ref_tol=0.05)
 
 
