@@ -329,6 +329,16 @@ typedef struct {
 } sdr_io_stats_t;
 int sdr_pipe_run_fd(sdr_pipe_t *p, sdr_pipe_t *sink, int in_fd, long long vec_len, long long max_vecs, int out_fd, int flags,
                     sdr_io_stats_t *stats);
+/* Stream state export / import (checkpoint / resume).  The state of a stage is what it carries between vectors: the
+ * not-yet-consumed tail of the input stream (the reference's crossover carry, Filter.hs:558-569, 600-611, 712-727), the
+ * resampler's counters ((group, offset), Filter.hs:419-424), fmDemod's last sample (Demod.hs:41-46), the dcBlocker pair
+ * (Filter.hs:731-739) and the outputs not yet popped (advanceOutBuf's partial block, Filter.hs:516-523).  save writes a
+ * self-describing blob to HOST memory (sdr_pipe_state_size bytes; synchronises the stage's stream); restore loads it
+ * into a stage constructed the same way (kind, taps, factors, block size -- checked, SDR_EINVAL otherwise).  The stream
+ * then continues bit for bit as if it had never been interrupted.  Connections are not part of the state. */
+int sdr_pipe_state_size(sdr_pipe_t *p, size_t *bytes);
+int sdr_pipe_state_save(sdr_pipe_t *p, void *buf, size_t capacity, size_t *written);
+int sdr_pipe_state_restore(sdr_pipe_t *p, const void *buf, size_t bytes);
 /* connect: everything `src` yields is pushed into `dst` device-to-device without touching the host (>->) */
 int sdr_pipe_connect(sdr_pipe_t *src, sdr_pipe_t *dst);
 
@@ -362,7 +372,7 @@ int sdr_comm_barrier(sdr_comm_t *c);
  * maps its right neighbour's chunk.  sdr_decimate_sharded on that same d_in is then ONE launch: the ring kernel's edge
  * fills read the T-D halo samples in place from the neighbour's HBM over NVLink (TMA bulk copies of peer memory; no
  * per-pass NCCL kernel, no rendezvous).  The caller guarantees the neighbour's chunk is complete before a pass starts. */
-int sdr_comm_share_chunks(sdr_comm_t *c, const void *d_chunk_base);
+int sdr_comm_share_chunks(sdr_comm_t *c, const void *d_chunk_base); /* NULL: drop the mapping (local call), NCCL transport again */
 int sdr_comm_peer_halo_active(const sdr_comm_t *c, const void *d_in);
 /* one pass of the sharded decimator: interior outputs on the ctx stream, halo exchange (ncclSend of my first
  * `halo` samples to rank-1 / ncclRecv from rank+1) on a side stream, boundary outputs after the halo lands.

@@ -162,6 +162,9 @@ _sig("sdr_pipe_push", _P, _P, _LL, _I)
 _sig("sdr_pipe_ready", _P, C.POINTER(_I))
 _sig("sdr_pipe_pop", _P, _P, C.POINTER(_LL), _I)
 _sig("sdr_pipe_connect", _P, _P)
+_sig("sdr_pipe_state_size", _P, C.POINTER(_SZ))
+_sig("sdr_pipe_state_save", _P, _P, _SZ, C.POINTER(_SZ))
+_sig("sdr_pipe_state_restore", _P, _P, _SZ)
 _sig("sdr_pipe_sync", _P)
 _sig("sdr_pipe_set_batch", _P, _LL)
 _sig("sdr_pipe_next_len", _P, C.POINTER(_LL))

@@ -37,8 +37,7 @@ struct Ctx {
     int          arith       = SDR_ARITH_FAST;
     bool         fir_ffa     = false;    // real stride-1 filters: 2-parallel fast-FIR arithmetic (kernels_real.cu)
     long long    launches    = 0;
-    // pinned + device staging for HOST-pointer calls (grown on demand)
-    void  *h_stage = nullptr; size_t h_stage_bytes = 0;
+    // device staging for HOST-pointer calls (grown on demand; copies go straight from / to the caller's memory)
     void  *d_stage_in = nullptr; size_t d_stage_in_bytes = 0;
     void  *d_stage_out = nullptr; size_t d_stage_out_bytes = 0;
     void  *d_flush = nullptr; size_t d_flush_bytes = 0;

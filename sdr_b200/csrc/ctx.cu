@@ -52,8 +52,6 @@ static int grow(void **p, size_t *have, size_t want, bool pinned) {
 }
 
 int Ctx::ensure_stage(size_t in_bytes, size_t out_bytes) {
-    // pinned staging holds input and output back to back so one buffer serves both directions
-    SDR_TRY(grow(&h_stage, &h_stage_bytes, in_bytes + out_bytes + 256, true));
     SDR_TRY(grow(&d_stage_in, &d_stage_in_bytes, in_bytes + 256, false));
     SDR_TRY(grow(&d_stage_out, &d_stage_out_bytes, out_bytes + 256, false));
     return SDR_OK;
@@ -110,7 +108,7 @@ int sdr_has_cuda(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     for (int i = 0; i < n; i++) {
         cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) return 1;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10 && p.minor == 0) return 1;   // sm_100a code only
     }
     return 0;
 }
@@ -123,7 +121,7 @@ int sdr_ctx_create(int device, sdr_ctx_t **ctx) {
     if (device < 0 || device >= n) return set_error(SDR_EINVAL, "sdr_ctx_create: device %d out of range (%d)", device, n);
     cudaDeviceProp p;
     SDR_CUDA(cudaGetDeviceProperties(&p, device));
-    if (p.major != 10)
+    if (p.major != 10 || p.minor != 0)
         return set_error(SDR_ENODEVICE, "device %d (%s, sm_%d%d) is not sm_100: this library carries sm_100a code only",
                          device, p.name, p.major, p.minor);
     Ctx *c = new Ctx();
@@ -145,7 +143,6 @@ int sdr_ctx_destroy(sdr_ctx_t *ctx) {
     SDR_TRY(c->bind());
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->side);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->d_stage_in) cudaFree(c->d_stage_in);
     if (c->d_stage_out) cudaFree(c->d_stage_out);
     if (c->d_flush) cudaFree(c->d_flush);

@@ -170,11 +170,15 @@ int sdr_comm_destroy(sdr_comm_t *c) {
 // NVLink inside the boundary launch: no NCCL kernel per pass, no rendezvous, no SMs set aside.  The caller guarantees
 // that the neighbour's chunk is complete before a pass starts (e.g. a barrier after producing it).
 int sdr_comm_share_chunks(sdr_comm_t *c, const void *d_chunk_base) {
-    if (!c || !d_chunk_base) return set_error(SDR_EINVAL, "sdr_comm_share_chunks: bad argument");
+    if (!c) return set_error(SDR_EINVAL, "sdr_comm_share_chunks: bad argument");
     Ctx *ctx = c->ctx;
     SDR_TRY(ctx->bind());
-    if (c->peer_base) { cudaIpcCloseMemHandle(c->peer_base); c->peer_base = nullptr; }
+    if (c->peer_base) {
+        SDR_CUDA(cudaStreamSynchronize(ctx->stream));   // no pass may still be reading through the mapping
+        cudaIpcCloseMemHandle(c->peer_base); c->peer_base = nullptr;
+    }
     c->my_base = nullptr;
+    if (!d_chunk_base) return SDR_OK;   // NULL: drop the mapping, back to the NCCL transport (local, not a collective)
     if (c->world == 1) return SDR_OK;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t mine;

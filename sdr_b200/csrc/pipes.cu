@@ -127,6 +127,9 @@ struct sdr_pipe {
     int last_sel = 0;                 // which half of the double-buffered carried sample is current
     const char *last_kernel = "none";
     sdr_pipe *downstream = nullptr;
+    sdr_pipe *upstream = nullptr;     // the stage connected in front of this one (unlinked when either side is destroyed)
+    long long skip = 0;               // input elements still to drop: a decimation factor larger than the tap count skips
+                                      // past the resident data (the reference's VG.drop (count*D - len), Filter.hs:610)
     const char *assert_name = "";
     // SDR_HOST_PINNED pushes: host-to-device copies of vectors that are contiguous on both sides are merged and
     // issued only when a launch needs the data (one DMA per output vector instead of one per input vector)
@@ -251,7 +254,11 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     }
     p->last_sel ^= 1;
     p->fifo.wr += (size_t)count * 4;
-    p->in.rd += (size_t)(count * f.D) * 2;
+    {
+        const long long adv = count * f.D < have ? count * f.D : have;
+        p->skip += 2 * (count * f.D - adv);
+        p->in.rd += (size_t)adv * 2;
+    }
     if (p->in.size() <= (1u << 16) && p->in.rd > p->in.cap / 4) SDR_TRY(p->in.realign(0));
     return SDR_OK;
 }
@@ -281,7 +288,11 @@ static int process_u8_decim(sdr_pipe *p, long long fifo_have, long long batch) {
         SDR_TRY(f.run(seg, 0, out, count, false));
     }
     p->fifo.wr += (size_t)count * 8;
-    p->in.rd += (size_t)(count * f.D) * 2;
+    {
+        const long long adv = count * f.D < have ? count * f.D : have;
+        p->skip += 2 * (count * f.D - adv);
+        p->in.rd += (size_t)adv * 2;
+    }
     if (p->in.size() <= (1u << 16) && p->in.rd > p->in.cap / 4) SDR_TRY(p->in.realign(0));
     return SDR_OK;
 }
@@ -333,7 +344,11 @@ static int process_fir(sdr_pipe *p, bool force = false) {
         Seg2 seg = {p->in.p + p->in.rd, have, nullptr, 0};
         SDR_TRY(f.run(seg, 0, p->fifo.p + p->fifo.wr, count, false));
         p->fifo.wr += (size_t)count * p->out_eb;
-        p->in.rd += (size_t)(count * f.D) * p->in_eb;
+        {
+            const long long adv = count * f.D < have ? count * f.D : have;
+            p->skip += count * f.D - adv;
+            p->in.rd += (size_t)adv * p->in_eb;
+        }
         // park the short tail at the front right after a launch: keeps the tuned kernels' 16-byte alignment and means
         // the buffer never has to slide while it holds a half-collected batch
         if (p->in.size() <= (1u << 16) && ((p->in.rd & 15) || p->in.rd > p->in.cap / 4)) SDR_TRY(p->in.realign(0));
@@ -381,11 +396,16 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, lon
         }
         if (n < need) return set_error(SDR_EPRECOND, "%s 1: input vector of %lld elements is shorter than numCoeffs (%lld)",
                                        p->assert_name, n, need);
+        p->n_total += n;
+        if (p->skip > 0) {   // samples a large decimation factor has already stepped over
+            const long long d = p->skip < n ? p->skip : n;
+            src = (const char *)src + (size_t)d * p->in_eb; n -= d; p->skip -= d;
+            if (n == 0) return SDR_OK;
+        }
         if (p->in.wr + (size_t)n * p->in_eb > p->in.cap) SDR_TRY(flush_pending(p));   // the buffer is about to move
         SDR_TRY(p->in.reserve((size_t)n * p->in_eb));
         SDR_TRY(fetch(p, p->in.p + p->in.wr, src, (size_t)n * p->in_eb, mem));
         p->in.wr += (size_t)n * p->in_eb;
-        p->n_total += n;
         SDR_TRY(process_fir(p));
         return forward(p);
     }
@@ -509,6 +529,9 @@ int sdr_pipe_destroy(sdr_pipe_t *p) {
     p->ctx->bind();
     cudaStreamSynchronize(p->ctx->stream);
     cudaStreamSynchronize(p->ctx->side);
+    // unlink: a neighbour that outlives this stage must not forward into (or be unlinked from) freed memory
+    if (p->upstream) p->upstream->downstream = nullptr;
+    if (p->downstream) p->downstream->upstream = nullptr;
     p->in.release(); p->fifo.release(); p->bnd.release(); p->scratch_x.release(); p->scratch_y.release();
     if (p->d_last) cudaFree(p->d_last);
     if (p->ev_out_ready) cudaEventDestroy(p->ev_out_ready);
@@ -582,12 +605,118 @@ int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs) {
     if (is_fir_kind(p->kind) && min_outputs > 0) {
         // size both buffers for the batch once, instead of growing by doubling while the stream runs
         SDR_TRY(p->ctx->bind());
+        SDR_TRY(flush_pending(p));    // a reserve may slide or reallocate: no deferred copy may still target the old place,
+        SDR_TRY(fifo_writable(p));    // and no in-flight drain may still be reading it
         long long in_per_out = (p->kind == P_RESAMP) ? (p->res->M + p->res->L - 1) / p->res->L
                              : is_byte_fed(p->kind) ? 2 * p->fir->D : p->fir->D;
         long long taps = (p->kind == P_RESAMP) ? p->res->T : p->fir->T;
         SDR_TRY(p->in.reserve((size_t)(2 * (min_outputs + p->block_out) * in_per_out + taps) * p->in_eb));
         SDR_TRY(p->fifo.reserve((size_t)(2 * (min_outputs + p->block_out)) * p->out_eb));
     }
+    return SDR_OK;
+}
+
+// ---- stream state export / import (SURVEY.md section 5 "checkpoint / resume", section 8b-ii) -------------------------------
+// What a stage carries between vectors, and therefore what a checkpoint holds:
+//   FIR kinds     the not-yet-consumed tail of the input stream (< numCoeffs samples plus what a batching threshold is
+//                 still holding back) -- the reference's `crossover` carry (Filter.hs:558-569, 600-611, 712-727);
+//   resampler     + the global output / input counters from which (group, offset) follow in closed form (Filter.hs:419-424);
+//   fmDemod       the previous buffer's last sample (Demod.hs:41-46);  fused FM front end: the last decimated sample;
+//   dcBlocker     (lastSample, lastOutput) (Filter.hs:731-739);
+//   every kind    outputs produced but not yet popped (the partially filled output block of advanceOutBuf, Filter.hs:516-523).
+namespace {
+struct StateHeader {
+    uint32_t magic, version;
+    int32_t  kind, in_eb, out_eb, taps, factor, interp, last_sel, reserved;
+    int64_t  block_out, k_next, pos, n_total, skip, in_bytes, fifo_bytes, n_vecs, last_bytes;
+};
+const uint32_t STATE_MAGIC = 0x50524453u;   // "SDRP"
+size_t last_bytes_of(const sdr_pipe *p) {
+    if (!p->d_last) return 0;
+    return p->kind == P_FMFRONT ? 16 : 8;
+}
+void fill_header(const sdr_pipe *p, StateHeader *h) {
+    memset(h, 0, sizeof(*h));
+    h->magic = STATE_MAGIC; h->version = 1; h->kind = p->kind; h->in_eb = (int32_t)p->in_eb; h->out_eb = (int32_t)p->out_eb;
+    if (p->fir) { h->taps = p->fir->T; h->factor = p->fir->D; h->interp = 1; }
+    if (p->res) { h->taps = p->res->T; h->factor = p->res->M; h->interp = p->res->L; }
+    h->last_sel = p->last_sel; h->block_out = p->block_out; h->k_next = p->k_next; h->pos = p->pos; h->n_total = p->n_total;
+    h->skip = p->skip; h->in_bytes = is_fir_kind(p->kind) ? (int64_t)p->in.size() : 0; h->fifo_bytes = (int64_t)p->fifo.size();
+    h->n_vecs = (int64_t)p->vec_lens.size(); h->last_bytes = (int64_t)last_bytes_of(p);
+}
+size_t state_bytes(const StateHeader &h) {
+    return sizeof(StateHeader) + (size_t)h.in_bytes + (size_t)h.fifo_bytes + (size_t)h.n_vecs * 8 + (size_t)h.last_bytes;
+}
+}  // namespace
+
+int sdr_pipe_state_size(sdr_pipe_t *p, size_t *bytes) {
+    if (!p || !bytes) return set_error(SDR_EINVAL, "sdr_pipe_state_size: bad argument");
+    StateHeader h;
+    fill_header(p, &h);
+    *bytes = state_bytes(h);
+    return SDR_OK;
+}
+
+int sdr_pipe_state_save(sdr_pipe_t *p, void *buf, size_t capacity, size_t *written) {
+    if (!p || !buf) return set_error(SDR_EINVAL, "sdr_pipe_state_save: bad argument");
+    SDR_TRY(p->ctx->bind());
+    SDR_TRY(flush_pending(p));
+    SDR_TRY(fifo_writable(p));
+    StateHeader h;
+    fill_header(p, &h);
+    const size_t need = state_bytes(h);
+    if (capacity < need) return set_error(SDR_EINVAL, "sdr_pipe_state_save: %zu bytes needed, %zu given", need, capacity);
+    char *q = (char *)buf;
+    memcpy(q, &h, sizeof(h)); q += sizeof(h);
+    cudaStream_t st = p->ctx->stream;
+    if (h.in_bytes) SDR_CUDA(cudaMemcpyAsync(q, p->in.p + p->in.rd, (size_t)h.in_bytes, cudaMemcpyDeviceToHost, st));
+    q += h.in_bytes;
+    if (h.fifo_bytes) SDR_CUDA(cudaMemcpyAsync(q, p->fifo.p + p->fifo.rd, (size_t)h.fifo_bytes, cudaMemcpyDeviceToHost, st));
+    q += h.fifo_bytes;
+    for (long long n : p->vec_lens) { int64_t v = n; memcpy(q, &v, 8); q += 8; }
+    if (h.last_bytes) SDR_CUDA(cudaMemcpyAsync(q, p->d_last, (size_t)h.last_bytes, cudaMemcpyDeviceToHost, st));
+    SDR_CUDA(cudaStreamSynchronize(st));
+    SDR_CUDA(cudaStreamSynchronize(p->ctx->side));
+    if (written) *written = need;
+    return SDR_OK;
+}
+
+// into a stage constructed the same way (same kind, taps / factors, block size); whatever it held is discarded
+int sdr_pipe_state_restore(sdr_pipe_t *p, const void *buf, size_t bytes) {
+    if (!p || !buf || bytes < sizeof(StateHeader)) return set_error(SDR_EINVAL, "sdr_pipe_state_restore: bad argument");
+    StateHeader h, mine;
+    memcpy(&h, buf, sizeof(h));
+    fill_header(p, &mine);
+    if (h.magic != STATE_MAGIC || h.version != 1) return set_error(SDR_EINVAL, "sdr_pipe_state_restore: not a pipe state (magic / version)");
+    if (h.kind != mine.kind || h.in_eb != mine.in_eb || h.out_eb != mine.out_eb || h.taps != mine.taps || h.factor != mine.factor ||
+        h.interp != mine.interp || h.block_out != mine.block_out || h.last_bytes != mine.last_bytes)
+        return set_error(SDR_EINVAL, "sdr_pipe_state_restore: the state was saved from a differently constructed stage "
+                         "(kind %d/%d, taps %d/%d, factor %d/%d, block %lld/%lld)", h.kind, mine.kind, h.taps, mine.taps, h.factor,
+                         mine.factor, (long long)h.block_out, (long long)mine.block_out);
+    if (h.in_bytes < 0 || h.fifo_bytes < 0 || h.n_vecs < 0 || bytes < state_bytes(h))
+        return set_error(SDR_EINVAL, "sdr_pipe_state_restore: truncated state (%zu bytes)", bytes);
+    SDR_TRY(p->ctx->bind());
+    SDR_TRY(flush_pending(p));
+    SDR_TRY(fifo_writable(p));
+    cudaStream_t st = p->ctx->stream;
+    const char *q = (const char *)buf + sizeof(h);
+    p->in.rd = p->in.wr = 0; p->fifo.rd = p->fifo.wr = 0; p->vec_lens.clear();
+    if (h.in_bytes) {
+        SDR_TRY(p->in.reserve((size_t)h.in_bytes));
+        SDR_CUDA(cudaMemcpyAsync(p->in.p, q, (size_t)h.in_bytes, cudaMemcpyHostToDevice, st));
+        p->in.wr = (size_t)h.in_bytes;
+    }
+    q += h.in_bytes;
+    if (h.fifo_bytes) {
+        SDR_TRY(p->fifo.reserve((size_t)h.fifo_bytes));
+        SDR_CUDA(cudaMemcpyAsync(p->fifo.p, q, (size_t)h.fifo_bytes, cudaMemcpyHostToDevice, st));
+        p->fifo.wr = (size_t)h.fifo_bytes;
+    }
+    q += h.fifo_bytes;
+    for (int64_t i = 0; i < h.n_vecs; i++) { int64_t v; memcpy(&v, q, 8); q += 8; p->vec_lens.push_back(v); }
+    if (h.last_bytes) SDR_CUDA(cudaMemcpyAsync(p->d_last, q, (size_t)h.last_bytes, cudaMemcpyHostToDevice, st));
+    p->last_sel = h.last_sel; p->k_next = h.k_next; p->pos = h.pos; p->n_total = h.n_total; p->skip = h.skip;
+    SDR_CUDA(cudaStreamSynchronize(st));   // `buf` is the caller's again
     return SDR_OK;
 }
 
@@ -830,7 +959,11 @@ int sdr_pipe_connect(sdr_pipe_t *src, sdr_pipe_t *dst) {
             return set_error(SDR_EPRECOND, "%s 1: upstream vectors of %lld elements are shorter than numCoeffs (%lld)",
                              dst->assert_name, src->block_out, need);
     }
+    if (dst->upstream && dst->upstream != src)
+        return set_error(SDR_EINVAL, "sdr_pipe_connect: the destination stage already has an upstream stage");
+    if (src->downstream) src->downstream->upstream = nullptr;
     src->downstream = dst;
+    dst->upstream = src;
     return SDR_OK;
 }
 

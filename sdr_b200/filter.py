@@ -217,6 +217,7 @@ class NativePipe:
 
     def __init__(self, handle, ctx, in_dtype, out_dtype, owner=None):
         self.h, self.ctx, self.in_dtype, self.out_dtype, self.owner = handle, ctx, np.dtype(in_dtype), np.dtype(out_dtype), owner
+        self._down = None
 
     def push(self, vec):
         v = np.ascontiguousarray(vec, dtype=self.in_dtype)
@@ -234,14 +235,29 @@ class NativePipe:
         L.check(L.lib.sdr_pipe_pop(self.h, L.ptr(out), C.byref(n), L.SDR_HOST))
         return out[:n.value]
 
+    def state_save(self) -> bytes:
+        """sdr_pipe_state_save: the stage's carried stream state (tail, counters, carried samples, un-popped outputs)"""
+        n = C.c_size_t()
+        L.check(L.lib.sdr_pipe_state_size(self.h, C.byref(n)))
+        buf = (C.c_char * n.value)()
+        w = C.c_size_t()
+        L.check(L.lib.sdr_pipe_state_save(self.h, buf, n.value, C.byref(w)))
+        return bytes(buf[:w.value])
+
+    def state_restore(self, blob: bytes):
+        """sdr_pipe_state_restore into a stage constructed the same way"""
+        L.check(L.lib.sdr_pipe_state_restore(self.h, blob, len(blob)))
+
     def connect(self, dst):
         L.check(L.lib.sdr_pipe_connect(self.h, dst.h))
+        self._down = dst   # keep the downstream stage alive as long as this one can forward into it
         return dst
 
     def close(self):
         if self.h:
-            L.lib.sdr_pipe_destroy(self.h)
+            L.lib.sdr_pipe_destroy(self.h)   # also unlinks it from its neighbours (sdr_pipe_destroy)
             self.h = None
+        self._down = None
 
     def __del__(self):
         if L is not None:

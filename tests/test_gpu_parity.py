@@ -757,3 +757,20 @@ def test_ring_kernel_covers_two_segments_and_ragged_end(sdr, L, ctx, ref, n_last
     assert np.all(got[count:].view(np.uint32) == 0xffffffff), "stores past the last output"
     for buf in (a, b, y):
         buf.free()
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+def test_decimator_pipe_factor_larger_than_tap_count(sdr, cplx):
+    """decimation factor > numCoeffs: the next window starts beyond the resident samples.  The reference runs into its own
+    `decimate 3` assert there (Filter.hs:603); the pipe carries the samples still to skip into the following vectors and
+    keeps computing the flat-stream decimation y[m] = sum_k c[k] x[m D + k]."""
+    T, D, block_out = 16, 40, 50
+    sizes = [4096, 1000, 40, 17, 5000, 16, 3000]
+    taps = taps_for(T, 3)
+    x = rnd(sum(sizes), cplx, 8)
+    d = (sdr.cudaDecimatorC if cplx else sdr.cudaDecimatorR)(D, taps)
+    got = list(sdr.firDecimator(d, block_out, _chunks(x, sizes)))
+    total = (len(x) - T) // D + 1
+    assert len(got) == total // block_out and all(len(g) == block_out for g in got)
+    y = np.concatenate(got)
+    close(y, op.flat_decimate(x, taps, D, len(y)).astype(y.dtype))
