@@ -90,19 +90,22 @@ Ctx *default_ctx(int *status);   // per-thread context behind the reference-sign
 // complex data, real taps, decimate by D.  Returns SDR_OK and sets *done to the number of leading outputs it
 // produced (a multiple of its tile; 0 when the shape / alignment has no tuned kernel); the caller finishes the rest
 // with launch_fir_generic.  *name receives a static string naming the instantiation.
+// Padded-segment ring (kernels_fast.cu): real or complex data, decimation 4 / 8 / 16, up to 128 stored taps.
 // x = seg.a ++ seg.b.  When both sources and their boundary are 16-byte aligned the kernel covers ALL `num` outputs
-// (windows straddling the two segments and the ragged last tile included): *done == num.
-int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, Seg2 seg, float *d_out, long long num, long long *done,
-                      const char **name);
+// (windows straddling the two segments and the ragged last tile included): *done == num; otherwise *done = the leading
+// outputs it produced (a multiple of its tile; 0: no tuned kernel for the shape) and the caller finishes the rest with
+// launch_fir_generic.  d_taps must be zero-padded to at least 128 floats (FirRec does that).
+int launch_dec_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_taps, Seg2 seg, void *d_out, long long num,
+                    long long *done, const char **name);
 // opt a kernel in to `smem_bytes` of dynamic shared memory, once per (kernel, device)
 int ring_attr(Ctx *c, const void *kernel, int smem_bytes);
 
-// real data, stride-1 FIR (kernels_real.cu); same contract as launch_dec_c_fast
-int launch_fir_r_fast(Ctx *c, int T, int D, const float *d_taps, const float *d_in, long long n_in, float *d_out,
-                      long long num, long long *done, const char **name);
-// real rational resampler: output 0 is phase 0 and its window starts at d_in; d_plain_taps = the n_taps plain taps
-int launch_res_r_fast(Ctx *c, int L, int M, int n_taps, const float *d_plain_taps, const float *d_in, long long n_in,
-                      float *d_out, long long num, long long *done, const char **name);
+// contiguous-slot ring (kernels_real.cu): stride 1 (the filters) and 2, real or complex data, up to 128 stored taps
+int launch_fir_small_stride_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_taps, const void *d_in, long long n_in,
+                                 void *d_out, long long num, long long *done, const char **name);
+// rational resampler, real or complex data: output 0 is phase 0 and its window starts at d_in; d_plain_taps = the n_taps plain taps
+int launch_res_fast(Ctx *c, bool cplx, int L, int M, int n_taps, const float *d_plain_taps, const void *d_in, long long n_in,
+                    void *d_out, long long num, long long *done, const char **name);
 
 // fused u8 convert + decimate + FM demod of outputs [0, num) of a byte stream (kernels_fm.cu)
 int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,

@@ -20,16 +20,24 @@
 
 namespace sdr {
 
-template <int T, int D, int R>
+// One instantiation per (data type, stored tap count T, decimation D, outputs per lane R).  T is the kernel's tap
+// capacity: a record with fewer taps runs on the next larger instantiation with its tap array zero-padded (FirRec keeps
+// d_taps padded to 128 floats), so e.g. the FM example's 51-tap RF decimator (examples/fm/Coeffs.hs:11-66) is the <64, 8>
+// kernel.  T need not be a multiple of D.
+template <bool CPLX, int T, int D, int R>
 struct RingCfg {
-    static_assert(T % D == 0 && D % 2 == 0, "taps must be a whole number of decimation blocks; D even");
-    static constexpr int JB = T / D;                        // tap blocks per output
-    static constexpr int BLK_BYTES = D * 8;                 // one decimation block of complex samples
-    static constexpr int SEG_BYTES = R * BLK_BYTES;         // the R blocks a lane owns
+    static constexpr int EB = CPLX ? 8 : 4;                 // bytes per stream element
+    static constexpr int EPC = 16 / EB;                     // elements per 16-byte chunk (one LDS.128)
+    static constexpr int SEG_ELEMS = R * D;                 // the input elements a lane's R outputs advance over
+    static constexpr int SEG_BYTES = SEG_ELEMS * EB;
+    static_assert(SEG_BYTES % 16 == 0, "lane segments are moved by 16-byte bulk copies");
     static constexpr int SEG_STRIDE = SEG_BYTES + 16;       // +16 B: lanes' LDS.128 land on distinct bank groups
     static constexpr int SUB_OUT = 32 * R;                  // outputs per sub-tile (one warp pass)
     static constexpr int SLOT_BYTES = 32 * SEG_STRIDE;
-    static constexpr int HALO_SEGS = (JB - 1 + R - 1) / R;  // segments of the NEXT sub-tile a pass reads
+    static constexpr int WIN = (R - 1) * D + T;             // elements a lane reads
+    static constexpr int NCH = (WIN + EPC - 1) / EPC;       // ... as 16-byte chunks
+    static constexpr int HALO_RAW = (NCH * EPC - SEG_ELEMS + SEG_ELEMS - 1) / SEG_ELEMS;
+    static constexpr int HALO_SEGS = HALO_RAW < 1 ? 1 : HALO_RAW;   // segments of the NEXT sub-tile a pass reads
     static constexpr int NWARPS = 8;
     static constexpr int NS_FIT = (220 * 1024 - HALO_SEGS * SEG_STRIDE - 256) / SLOT_BYTES;
     static constexpr int NS = NS_FIT >= 2 * NWARPS ? 2 * NWARPS : NS_FIT;                  // ring slots
@@ -38,13 +46,14 @@ struct RingCfg {
     static constexpr int SMEM_BYTES = RING_BYTES + 2 * NS * 8 + NS * 4 + 256;
     static_assert(NS >= NWARPS + 3, "ring too small for 8 warps plus prefetch");
     static_assert(HALO_SEGS <= 32, "halo wider than a sub-tile");
+    static_assert(CPLX ? R % 2 == 0 : R % 4 == 0, "outputs per lane are stored in 16-byte groups");
 };
 
-template <int T, int D, int R>
+template <bool CPLX, int T, int D, int R>
 __global__ void __launch_bounds__(256, 1)
-k_dec_c_ring(const float2 *__restrict__ in, long long a_bytes, const float2 *__restrict__ in_b, long long total_bytes,
-             float2 *__restrict__ out, long long num, const float *__restrict__ taps, long long n_sub) {
-    typedef RingCfg<T, D, R> C;
+k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restrict__ in_b, long long total_bytes,
+           void *__restrict__ out, long long num, const float *__restrict__ taps, long long n_sub) {
+    typedef RingCfg<CPLX, T, D, R> C;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
@@ -70,8 +79,8 @@ k_dec_c_ring(const float2 *__restrict__ in, long long a_bytes, const float2 *__r
     const unsigned char *gin = reinterpret_cast<const unsigned char *>(in);
     // The stream is `in` (a_bytes bytes) followed by `in_b` (up to total_bytes; the right neighbour's chunk on a sharded
     // pass, or nothing); everything beyond total_bytes reads as zero.  A fill that lies wholly inside `in` -- all of them
-    // except the last one or two of the last CTA -- takes the fast path: one 512-byte bulk copy per lane.
-    constexpr long long SUB_BYTES = (long long)C::SUB_OUT * C::BLK_BYTES;
+    // except the last one or two of the last CTA -- takes the fast path: one bulk copy of a whole segment per lane.
+    constexpr long long SUB_BYTES = 32LL * C::SEG_BYTES;
     const long long cta_bytes = a_bytes - s0 * SUB_BYTES;
     const int fast_full = (int)(cta_bytes <= 0 ? 0 : (cta_bytes / SUB_BYTES > cnt ? cnt : cta_bytes / SUB_BYTES));
     const bool halo_fast = cta_bytes >= cnt * SUB_BYTES + C::HALO_SEGS * C::SEG_BYTES;
@@ -142,40 +151,64 @@ k_dec_c_ring(const float2 *__restrict__ in, long long a_bytes, const float2 *__r
         slot_wait<C::GUARD>(bar_full + 8 * slot2, gen_armed + 4 * slot2, (u + 1) / C::NS + 1);
 
         const unsigned char *base = smem + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE;
-        u64 acc[R];
+        const long long m0 = (s0 + u) * (long long)C::SUB_OUT + lane * R;
+        if (CPLX) {
+            u64 acc[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) acc[r] = 0ULL;
+            for (int r = 0; r < R; r++) acc[r] = 0ULL;
 #pragma unroll
-        for (int b = 0; b < R + C::JB - 1; b++) {
-            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(base + (b / R) * C::SEG_STRIDE + (b % R) * C::BLK_BYTES);
-            ulonglong2 v[D / 2];
+            for (int c = 0; c < C::NCH; c++) {
+                const int e0 = c * 2;
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(base + (e0 / C::SEG_ELEMS) * C::SEG_STRIDE + (e0 % C::SEG_ELEMS) * 8);
 #pragma unroll
-            for (int i = 0; i < D / 2; i++) v[i] = p[i];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int j = b - r;
-                if (j < 0 || j >= C::JB) continue;
-#pragma unroll
-                for (int i = 0; i < D / 2; i++) {
-                    acc[r] = ffma2(v[i].x, dup2(tap[j * D + 2 * i]), acc[r]);
-                    acc[r] = ffma2(v[i].y, dup2(tap[j * D + 2 * i + 1]), acc[r]);
+                for (int r = 0; r < R; r++) {
+                    const int k0 = e0 - r * D, k1 = e0 + 1 - r * D;
+                    if (k0 >= 0 && k0 < T) acc[r] = ffma2(v.x, dup2(tap[k0 < 0 ? 0 : (k0 >= T ? 0 : k0)]), acc[r]);
+                    if (k1 >= 0 && k1 < T) acc[r] = ffma2(v.y, dup2(tap[k1 < 0 ? 0 : (k1 >= T ? 0 : k1)]), acc[r]);
                 }
             }
-        }
-        const long long m0 = (s0 + u) * (long long)C::SUB_OUT + lane * R;
-        float2 *os = out + m0;
-        if (m0 + R > num) {   // ragged last sub-tile of the stream
-            u64 *o = reinterpret_cast<u64 *>(os);
+            u64 *os = reinterpret_cast<u64 *>(out) + m0;
+            if (m0 + R > num) {   // ragged last sub-tile of the stream
 #pragma unroll
-            for (int r = 0; r < R; r++) if (m0 + r < num) o[r] = acc[r];
-        } else if (vec_store) {
-            ulonglong2 *o = reinterpret_cast<ulonglong2 *>(os);
+                for (int r = 0; r < R; r++) if (m0 + r < num) os[r] = acc[r];
+            } else if (vec_store) {
+                ulonglong2 *o = reinterpret_cast<ulonglong2 *>(os);
 #pragma unroll
-            for (int r = 0; r < R; r += 2) o[r / 2] = make_ulonglong2(acc[r], acc[r + 1]);
-        } else {   // output only 8-byte aligned (a pipe's FIFO cursor after an odd number of outputs)
-            u64 *o = reinterpret_cast<u64 *>(os);
+                for (int r = 0; r < R; r += 2) o[r / 2] = make_ulonglong2(acc[r], acc[r + 1]);
+            } else {   // output only 8-byte aligned (a pipe's FIFO cursor after an odd number of outputs)
 #pragma unroll
-            for (int r = 0; r < R; r++) o[r] = acc[r];
+                for (int r = 0; r < R; r++) os[r] = acc[r];
+            }
+        } else {
+            float acc[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C::NCH; c++) {
+                const int e0 = c * 4;
+                const float4 v = *reinterpret_cast<const float4 *>(base + (e0 / C::SEG_ELEMS) * C::SEG_STRIDE + (e0 % C::SEG_ELEMS) * 4);
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const int k = e0 + i - r * D;
+                        if (k >= 0 && k < T) acc[r] = fmaf(tap[k < 0 ? 0 : (k >= T ? 0 : k)], e[i], acc[r]);
+                    }
+                }
+            }
+            float *os = reinterpret_cast<float *>(out) + m0;
+            if (m0 + R > num) {
+#pragma unroll
+                for (int r = 0; r < R; r++) if (m0 + r < num) os[r] = acc[r];
+            } else if (vec_store) {
+                float4 *o = reinterpret_cast<float4 *>(os);
+#pragma unroll
+                for (int r = 0; r < R; r += 4) o[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) os[r] = acc[r];
+            }
         }
 
         __syncwarp();
@@ -191,57 +224,78 @@ k_dec_c_ring(const float2 *__restrict__ in, long long a_bytes, const float2 *__r
     }
 }
 
-template <int T, int D, int R>
-static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, float *d_out, long long num, long long *done) {
-    typedef RingCfg<T, D, R> C;
-    static_assert(R % 2 == 0, "outputs per lane are stored in 16-byte pairs");
+template <bool CPLX, int T, int D, int R>
+static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long long num, long long *done) {
+    typedef RingCfg<CPLX, T, D, R> C;
+    constexpr int EB = C::EB, EPC = C::EPC;
     const long long n_in = seg.na + seg.nb;
-    const long long needed = (num - 1) * D + T;                 // samples the `num` outputs read
-    const long long needed2 = (needed + 1) & ~1LL;              // bulk copies move whole 16-byte units (two samples)
-    const long long usable = n_in & ~1LL;
+    const long long needed = (num - 1) * D + T;                    // elements the `num` outputs read (T = the kernel's tap capacity)
+    const long long needed2 = (needed + EPC - 1) / EPC * EPC;      // bulk copies move whole 16-byte units
+    const long long usable = n_in / EPC * EPC;
     long long n_sub, a_bytes, total_bytes;
     // COVERING mode: the kernel produces all `num` outputs, ragged last sub-tile and windows that run into the second
     // segment included (its edge fills split a lane segment between the two sources and zero-fill what lies beyond).
-    // It needs both sources and the boundary between them on 16-byte boundaries.
-    const bool covering = num > 0 && needed2 <= usable && (seg.na % 2) == 0 && (seg.nb == 0 || (((uintptr_t)seg.b) & 15) == 0);
+    // It needs both sources and the boundary between them on 16-byte boundaries.  The caller's outputs are valid for the
+    // record's own tap count, which may be smaller than T: windows may then reach up to T - taps elements past the
+    // resident data, where the zero-padded taps meet zero-filled shared memory.
+    const bool covering = num > 0 && (seg.na % EPC) == 0 && (seg.nb == 0 || (((uintptr_t)seg.b) & 15) == 0) && (n_in % EPC) == 0;
     if (covering) {
         n_sub = (num + C::SUB_OUT - 1) / C::SUB_OUT;
-        a_bytes = seg.na * 8;
-        total_bytes = usable * 8;
+        a_bytes = seg.na * EB;
+        total_bytes = usable * EB;
         if (total_bytes < a_bytes) a_bytes = total_bytes;
         *done = num;
     } else {
         // interior only: the sub-tiles whose whole window (halo segments included) is resident in the first segment
-        long long blocks_avail = seg.na / D;
-        long long by_in = (blocks_avail - C::HALO_SEGS * R) / C::SUB_OUT;
+        long long by_in = (seg.na / C::SEG_ELEMS - C::HALO_SEGS) / 32;
         n_sub = num / C::SUB_OUT;
         if (by_in < n_sub) n_sub = by_in;
         if (n_sub <= 0) { *done = 0; return SDR_OK; }
-        a_bytes = total_bytes = (seg.na * 8) & ~15LL;
+        a_bytes = total_bytes = (seg.na * EB) & ~15LL;
         *done = n_sub * C::SUB_OUT;
     }
+    (void)needed2;
     SDR_TRY(c->bind());
-    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_c_ring<T, D, R>), C::SMEM_BYTES));
+    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_ring<CPLX, T, D, R>), C::SMEM_BYTES));
     int sms = c->sm_count - c->reserve_sms;
     if (sms < 1) sms = 1;
     int grid = (int)(n_sub < sms ? n_sub : sms);
     const long long num_mask = covering ? num : n_sub * C::SUB_OUT;
-    k_dec_c_ring<T, D, R><<<grid, 256, C::SMEM_BYTES, c->s()>>>((const float2 *)seg.a, a_bytes, (const float2 *)seg.b, total_bytes,
-                                                                  (float2 *)d_out, num_mask, d_taps, n_sub);
+    k_dec_ring<CPLX, T, D, R><<<grid, 256, C::SMEM_BYTES, c->s()>>>(seg.a, a_bytes, seg.b, total_bytes, d_out, num_mask, d_taps, n_sub);
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     return SDR_OK;
 }
 
-int launch_dec_c_fast(Ctx *c, int T, int D, const float *d_taps, Seg2 seg, float *d_out, long long num, long long *done,
-                      const char **name) {
+// x = seg.a ++ seg.b.  taps_stored = the record's tap count (d_taps is zero-padded to at least 128 floats).
+int launch_dec_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_taps, Seg2 seg, void *d_out, long long num,
+                    long long *done, const char **name) {
     *done = 0;
-    *name = "fir_direct";
+    *name = cplx ? "fir_direct" : "fir_tile";
     if ((((uintptr_t)seg.a) & 15) != 0) return SDR_OK;   // TMA bulk copies need a 16-byte aligned source; any output alignment
-    if (T == 128 && D == 8) {
-        *name = "dec_c_ring<128,8,8>";
-        return launch_ring<128, 8, 8>(c, d_taps, seg, d_out, num, done);
-    }
+    const int T = taps_stored <= 32 ? 32 : taps_stored <= 64 ? 64 : taps_stored <= 128 ? 128 : 0;
+    if (T == 0) return SDR_OK;
+#define SDR_RING(CP, TT, DD, RR, label)                                                     \
+    if (cplx == CP && T == TT && D == DD) { *name = label; return launch_ring<CP, TT, DD, RR>(c, d_taps, seg, d_out, num, done); }
+    SDR_RING(true, 128, 8, 8, "dec_c_ring<128,8,8>")
+    SDR_RING(true, 64, 8, 8, "dec_c_ring<64,8,8>")
+    SDR_RING(true, 32, 8, 8, "dec_c_ring<32,8,8>")
+    SDR_RING(true, 128, 4, 8, "dec_c_ring<128,4,8>")
+    SDR_RING(true, 64, 4, 8, "dec_c_ring<64,4,8>")
+    SDR_RING(true, 32, 4, 8, "dec_c_ring<32,4,8>")
+    SDR_RING(true, 128, 16, 4, "dec_c_ring<128,16,4>")
+    SDR_RING(true, 64, 16, 4, "dec_c_ring<64,16,4>")
+    SDR_RING(true, 32, 16, 4, "dec_c_ring<32,16,4>")
+    SDR_RING(false, 128, 8, 16, "dec_r_ring<128,8,16>")
+    SDR_RING(false, 64, 8, 16, "dec_r_ring<64,8,16>")
+    SDR_RING(false, 32, 8, 16, "dec_r_ring<32,8,16>")
+    SDR_RING(false, 128, 4, 16, "dec_r_ring<128,4,16>")
+    SDR_RING(false, 64, 4, 16, "dec_r_ring<64,4,16>")
+    SDR_RING(false, 32, 4, 16, "dec_r_ring<32,4,16>")
+    SDR_RING(false, 128, 16, 8, "dec_r_ring<128,16,8>")
+    SDR_RING(false, 64, 16, 8, "dec_r_ring<64,16,8>")
+    SDR_RING(false, 32, 16, 8, "dec_r_ring<32,16,8>")
+#undef SDR_RING
     return SDR_OK;
 }
 

@@ -21,6 +21,8 @@
 #include "demod.cuh"
 #include "ring_common.cuh"
 
+#include <cstdio>
+
 namespace sdr {
 
 template <int T, int D, int R, int NW>
@@ -217,34 +219,55 @@ __global__ void __launch_bounds__(256) k_fm_front_fixup(float *__restrict__ out,
     }
 }
 
+// One launch of the fused kernel for tap capacity TK (the record's taps zero-padded up to it), D = 8.
+template <int TK, int NW, bool SYM, bool DEMOD>
+static int launch_front_inst(Ctx *c, const float *d_taps, const uint8_t *d_in, long long n_samples, float *d_out, long long num,
+                             float2 *d_bnd, float2 *d_carry_out, long long n_sub) {
+    typedef FmCfg<TK, 8, 8, NW> C;
+    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<TK, 8, 8, NW, SYM, DEMOD>), C::SMEM_BYTES));
+    int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
+    k_fm_front_ring<TK, 8, 8, NW, SYM, DEMOD><<<grid, 32 * NW, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / 8, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
+    c->launches++;
+    SDR_CUDA(cudaGetLastError());
+    return SDR_OK;
+}
+
+// picks the instantiation: 128 taps -- symmetric taps keep half of them in registers and run 16 warps, arbitrary taps 8
+// warps; 64 / 32 tap capacity (e.g. the FM example's 51-tap RF decimator, examples/fm/Coeffs.hs:11-66, zero-padded) --
+// 16 warps.  `label` receives the kernel's name without its prefix.
+template <bool DEMOD>
+static int launch_front_any(Ctx *c, int taps_stored, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
+                            float *d_out, long long num, float2 *d_bnd, float2 *d_carry_out, long long n_sub, const char **label) {
+    if (taps_stored > 64) {
+        if (symmetric && taps_stored == 128) { *label = "<128,8,8,sym,16w>"; return launch_front_inst<128, 16, true, DEMOD>(c, d_taps, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub); }
+        *label = "<128,8,8>";
+        return launch_front_inst<128, 8, false, DEMOD>(c, d_taps, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub);
+    }
+    if (taps_stored > 32) { *label = "<64,8,8,16w>"; return launch_front_inst<64, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub); }
+    *label = "<32,8,8,16w>";
+    return launch_front_inst<32, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub);
+}
+
 // Fused convert + decimate + demod of outputs [0, num) of a byte stream holding n_samples IQ pairs.  d_carry: previous
 // stream sample (re, im) on the device, read by the fix-up; d_carry_out receives the last decimated complex output;
 // d_bnd: scratch of 2 complex per sub-tile (ceil(num / 256) sub-tiles).  *done = num when the shape has a tuned kernel.
+// T = the record's stored tap count (d_taps zero-padded to >= 128 floats).
 int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
                     float *d_out, long long num, float2 *d_bnd, long long bnd_capacity_subtiles, const float2 *d_carry,
                     float2 *d_carry_out, long long *done, const char **name) {
     *done = 0;
     *name = "unfused";
-    if (T != 128 || D != 8 || num <= 0) return SDR_OK;
+    if (T > 128 || D != 8 || num <= 0) return SDR_OK;
     if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 3) != 0) return SDR_OK;
     if ((num - 1) * D + T > n_samples) return set_error(SDR_EINVAL, "launch_fm_front: %lld outputs need more than %lld samples", num, n_samples);
     const long long n_sub = (num + 255) / 256;
     if (bnd_capacity_subtiles < n_sub) return set_error(SDR_EINVAL, "launch_fm_front: boundary scratch too small");
     SDR_TRY(c->bind());
-    int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
-    if (symmetric) {
-        typedef FmCfg<128, 8, 8, 16> C;
-        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<128, 8, 8, 16, true>), C::SMEM_BYTES));
-        k_fm_front_ring<128, 8, 8, 16, true><<<grid, 512, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
-        *name = "fm_front_ring<128,8,8,sym,16w>";
-    } else {
-        typedef FmCfg<128, 8, 8, 8> C;
-        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<128, 8, 8, 8, false>), C::SMEM_BYTES));
-        k_fm_front_ring<128, 8, 8, 8, false><<<grid, 256, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
-        *name = "fm_front_ring<128,8,8>";
-    }
-    c->launches++;
-    SDR_CUDA(cudaGetLastError());
+    const char *label = "";
+    SDR_TRY(launch_front_any<true>(c, T, d_taps, symmetric, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub, &label));
+    static thread_local char nm[64];
+    snprintf(nm, sizeof(nm), "fm_front_ring%s", label);
+    *name = nm;
     long long fg = (n_sub + 255) / 256;
     if (fg > 4LL * c->sm_count) fg = 4LL * c->sm_count;
     k_fm_front_fixup<<<(int)fg, 256, 0, c->s()>>>(d_out, d_bnd, d_carry, n_sub, 256);
@@ -260,25 +283,16 @@ int launch_dec_u8(Ctx *c, int T, int D, const float *d_taps, bool symmetric, con
                   float *d_out, long long num, long long *done, const char **name) {
     *done = 0;
     *name = "unfused";
-    if (T != 128 || D != 8 || num <= 0) return SDR_OK;
+    if (T > 128 || D != 8 || num <= 0) return SDR_OK;
     if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 7) != 0) return SDR_OK;
     if ((num - 1) * D + T > n_samples) return set_error(SDR_EINVAL, "launch_dec_u8: %lld outputs need more than %lld samples", num, n_samples);
     const long long n_sub = (num + 255) / 256;
     SDR_TRY(c->bind());
-    int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
-    if (symmetric) {
-        typedef FmCfg<128, 8, 8, 16> C;
-        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<128, 8, 8, 16, true, false>), C::SMEM_BYTES));
-        k_fm_front_ring<128, 8, 8, 16, true, false><<<grid, 512, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, nullptr, nullptr, d_taps, n_sub);
-        *name = "dec_u8_ring<128,8,8,sym,16w>";
-    } else {
-        typedef FmCfg<128, 8, 8, 8> C;
-        SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<128, 8, 8, 8, false, false>), C::SMEM_BYTES));
-        k_fm_front_ring<128, 8, 8, 8, false, false><<<grid, 256, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / D, d_out, num, nullptr, nullptr, d_taps, n_sub);
-        *name = "dec_u8_ring<128,8,8>";
-    }
-    c->launches++;
-    SDR_CUDA(cudaGetLastError());
+    const char *label = "";
+    SDR_TRY(launch_front_any<false>(c, T, d_taps, symmetric, d_in, n_samples, d_out, num, nullptr, nullptr, n_sub, &label));
+    static thread_local char nm[64];
+    snprintf(nm, sizeof(nm), "dec_u8_ring%s", label);
+    *name = nm;
     *done = num;
     return SDR_OK;
 }

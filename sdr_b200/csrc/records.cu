@@ -56,8 +56,11 @@ int FirRec::create(Ctx *c, bool is_complex, int factor, const float *coeffs, int
     }
     symmetric = true;
     for (int k = 0; k < T / 2; k++) if (memcmp(&full[k], &full[T - 1 - k], sizeof(float)) != 0) { symmetric = false; break; }
-    SDR_CUDA(cudaMalloc(&d_taps, sizeof(float) * T));
-    SDR_CUDA(cudaMemcpyAsync(d_taps, full.data(), sizeof(float) * T, cudaMemcpyHostToDevice, c->stream));
+    // the tuned kernels are instantiated for 32 / 64 / 128 taps and read their whole capacity: zero-padded on the device
+    const int t_alloc = round_up(T, 128) + 128;
+    full.resize(t_alloc, 0.0f);
+    SDR_CUDA(cudaMalloc(&d_taps, sizeof(float) * t_alloc));
+    SDR_CUDA(cudaMemcpyAsync(d_taps, full.data(), sizeof(float) * t_alloc, cudaMemcpyHostToDevice, c->stream));
     // EXACT: the AVX member of the family (CPUID.hs:100-104 picks AVX first)
     if (sym_half) { ex_W = 8; ex_layout = cplx ? 2 : 0; ex_sym = 1; ex_T = n; }
     else          { ex_W = 8; ex_layout = cplx ? 1 : 0; ex_sym = 0; ex_T = T; }
@@ -94,8 +97,8 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
         // on the side stream concurrently with the tuned kernel (fork before, join after).
         if (can_fork) SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
         const char *name = nullptr;
-        if (cplx) SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, seg, (float *)d_out, num, &done, &name));
-        else      SDR_TRY(launch_fir_r_fast(ctx, T, D, d_taps, (const float *)seg.a, seg.na, (float *)d_out, num, &done, &name));
+        if (D <= 2) SDR_TRY(launch_fir_small_stride_fast(ctx, cplx, T, D, d_taps, seg.a, seg.na, d_out, num, &done, &name));
+        else        SDR_TRY(launch_dec_fast(ctx, cplx, T, D, d_taps, seg, d_out, num, &done, &name));
         if (done > 0) last_kernel = name;
     }
     if (done < num) {
@@ -118,10 +121,15 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
 
 int FirRec::run_tuned(const void *d_in, long long n_in, long long first, void *d_out, long long num, long long *done) {
     *done = 0;
-    if (num <= 0 || !cplx || arith != SDR_ARITH_FAST) return SDR_OK;
+    if (num <= 0 || D <= 2 || arith != SDR_ARITH_FAST) return SDR_OK;
     const char *name = nullptr;
-    Seg2 seg = {(const char *)d_in + first * 8, n_in - first, nullptr, 0};
-    SDR_TRY(launch_dec_c_fast(ctx, T, D, d_taps, seg, (float *)d_out, num, done, &name));
+    // second segment with zero elements: keeps the kernel in its interior-only mode unless the whole request is resident
+    Seg2 seg = {(const char *)d_in + first * elem_bytes(cplx), n_in - first, nullptr, 0};
+    if ((num - 1) * (long long)D + T > seg.na) {   // not everything is resident: interior sub-tiles only
+        long long fit = seg.na >= T ? (seg.na - T) / D + 1 : 0;
+        if (fit < num) num = fit;
+    }
+    SDR_TRY(launch_dec_fast(ctx, cplx, T, D, d_taps, seg, d_out, num, done, &name));
     if (*done > 0) last_kernel = name;
     return SDR_OK;
 }
@@ -199,19 +207,19 @@ int ResRec::run(Seg2 seg, long long first, int g0, void *d_out, long long num, b
     // tuned kernel for real streams: it starts on a cycle boundary (phase 0) with a 16-byte aligned window, so a short
     // generic prefix brings the stream there, the tuned kernel takes the bulk, the generic kernel the ragged end
     static const bool no_tuned = getenv("SDR_B200_NOTUNED") != nullptr;   // debugging aid
-    if (!cplx && ng == L && num >= 4096 && !no_tuned) {
+    if (ng == L && num >= 4096 && !no_tuned) {
         auto span = [&](long long count) { long long gi = (long long)g0 + count;
                                            return (gi / ng) * sum_inc + prefix[gi % ng] - prefix[g0]; };
         long long p0 = -1;
         for (long long p = 0; p <= 4LL * ng; p++)
-            if ((g0 + p) % ng == 0 && span(p) < seg.na && ((((uintptr_t)seg.a) + (size_t)span(p) * 4) & 15) == 0) { p0 = p; break; }
+            if ((g0 + p) % ng == 0 && span(p) < seg.na && ((((uintptr_t)seg.a) + (size_t)span(p) * eb) & 15) == 0) { p0 = p; break; }
         if (p0 >= 0 && p0 < num) {
             long long done = 0;
             const char *name = nullptr;
             const bool can_fork = ctx->override_st == nullptr;
             if (can_fork) SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
-            SDR_TRY(launch_res_r_fast(ctx, L, M, n_taps, d_plain, (const float *)seg.a + span(p0), seg.na - span(p0),
-                                      (float *)d_out + p0, num - p0, &done, &name));
+            SDR_TRY(launch_res_fast(ctx, cplx, L, M, n_taps, d_plain, (const char *)seg.a + (size_t)span(p0) * eb, seg.na - span(p0),
+                                    (char *)d_out + (size_t)p0 * eb, num - p0, &done, &name));
             if (done > 0) {
                 last_kernel = name;
                 const bool fork = can_fork;
@@ -267,11 +275,12 @@ static int oneshot_fir(const char *who, int kind, bool cplx, int num, int factor
     else                    { T = numCoeffs; full.assign(coeffs, coeffs + numCoeffs); }
     const size_t eb = elem_bytes(cplx);
     long long n_in = (long long)(num - 1) * factor + T;
-    size_t taps_bytes = ((sizeof(float) * T + 255) / 256) * 256;
+    full.resize(round_up(T, 128) + 128, 0.0f);   // zero-padded: the tuned kernels read their whole tap capacity
+    size_t taps_bytes = ((sizeof(float) * full.size() + 255) / 256) * 256;
     size_t in_bytes = (size_t)n_in * eb, out_bytes = (size_t)num * eb;
     SDR_TRY(c->ensure_stage(taps_bytes + in_bytes, out_bytes));
     char *d_base = (char *)c->d_stage_in;
-    SDR_CUDA(cudaMemcpyAsync(d_base, full.data(), sizeof(float) * T, cudaMemcpyHostToDevice, c->stream));
+    SDR_CUDA(cudaMemcpyAsync(d_base, full.data(), sizeof(float) * full.size(), cudaMemcpyHostToDevice, c->stream));
     SDR_CUDA(cudaMemcpyAsync(d_base + taps_bytes, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
     FirRec r;
     r.ctx = c; r.cplx = cplx; r.D = factor; r.T = T; r.d_taps = (float *)d_base; r.d_ex_taps = r.d_taps;
