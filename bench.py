@@ -810,34 +810,47 @@ def run_configs(args, ctx, dec, sdr_b200, L, peak):
     put("dcBlocker", "dcBlocker (filter.c:152), chunk-parallel speculation, bit-exact, per float", ms, nr, 8.0, 0,
         "k_dc_spec_tiles + k_dc_repair" if par else "k_dc_blocker")
     d_fin.free()
-    # cfg4: the whole FM chain, u8 IQ in -> audio out, connected device pipes, 32 MiB pushes (16 Mi IQ pairs each)
+    # cfg4: the whole FM chain, u8 IQ in -> audio out, 32 MiB pushes (16 Mi IQ pairs each) of device-resident vectors read in
+    # place (SDR_DEVICE_HELD): two fused stages = front end (+ its 1-in-256 fix-up) and low-rate end per push
     fil = sdr_b200.cudaFilterSymR(half, ctx=ctx)
-    fe = sdr_b200.pipeFmFrontEnd(dec, BUF)
-    p3 = sdr_b200.pipeFirResampler(r, BUF)
-    p4 = sdr_b200.pipeFirFilter(fil, BUF)
-    p5 = sdr_b200.pipeScale(0.2, ctx)
-    fe.connect(p3).connect(p4).connect(p5)
-    for p in (fe, p3, p4):
-        L.check(L.lib.sdr_pipe_set_batch(p.h, 1 << 21))
     n_out = C.c_longlong()
     push = 1 << 25
 
-    def chain():
-        L.check(L.lib.sdr_pipe_run(fe.h, p5.h, bbuf.ptr, push, nbytes // push, L.SDR_DEVICE, y.ptr, 2 * n, L.SDR_DEVICE, C.byref(n_out)))
-    l0 = ctx.launches
-    ms = timed(chain, steps=4, warm=2)
-    put("cfg4_chain", "full FM pipe: u8 IQ -> convert -> decimate-by-8 (128 taps) -> fmDemod -> resample 3/10 (90 taps) -> 64-tap filter -> x0.2, "
-        "connected device pipes, 32 MiB pushes; per input IQ sample", ms, n, 2.15, 32 + 9 / 8 + 64 * 3 / 80, L.lib.sdr_pipe_last_kernel(fe.h).decode() + " + low-rate stages")
-    out["cfg4_chain"]["launches_per_pass"] = (ctx.launches - l0) / 6
-    out["cfg4_chain"]["audio_samples_out"] = int(n_out.value)
-    for p in (fe, p3, p4, p5):
-        p.close()
+    def time_chain(stages, label, key):
+        for a, b in zip(stages, stages[1:]):
+            a.connect(b)
+        for p in stages:
+            try:
+                L.check(L.lib.sdr_pipe_set_batch(p.h, 1 << 21))
+            except sdr_b200.SdrError:
+                pass
+
+        def chain():
+            L.check(L.lib.sdr_pipe_run(stages[0].h, stages[-1].h, bbuf.ptr, push, nbytes // push, L.SDR_DEVICE_HELD, y.ptr, 2 * n, L.SDR_DEVICE,
+                                       C.byref(n_out)))
+        for _ in range(2):
+            chain()
+        ctx.sync()
+        l0 = ctx.launches
+        ms = timed(chain, steps=4, warm=0)
+        put(key, label, ms, n, 2.15, 32 + 9 / 8 + 64 * 3 / 80, " + ".join(
+            k for k in (L.lib.sdr_pipe_last_kernel(st.h).decode() for st in stages) if k != "none"))
+        out[key]["launches_per_push"] = (ctx.launches - l0) / 4 / (nbytes // push)
+        out[key]["audio_samples_out"] = int(n_out.value)
+        for p in stages:
+            p.close()
+
+    time_chain([sdr_b200.pipeFmFrontEnd(dec, BUF), sdr_b200.pipeFmLowRate(r, BUF, fil, BUF, 0.2)],
+               "full FM pipe: u8 IQ -> [convert + decimate-by-8 (128 taps) + fmDemod] -> [resample 3/10 (90 taps) + 64-tap filter + x0.2], two fused "
+               "stages, 32 MiB device pushes read in place; per input IQ sample", "cfg4_chain")
+    time_chain([sdr_b200.pipeFmFrontEnd(dec, BUF), sdr_b200.pipeFirResampler(r, BUF), sdr_b200.pipeFirFilter(fil, BUF), sdr_b200.pipeScale(0.2, ctx)],
+               "the same chain with the low-rate end as three separate stages (round 1's form)", "cfg4_chain_unfused_lowrate")
     # the fused front end alone (u8 IQ -> phase)
     fe = sdr_b200.pipeFmFrontEnd(dec, BUF)
     L.check(L.lib.sdr_pipe_set_batch(fe.h, 1 << 23))
 
     def front():
-        L.check(L.lib.sdr_pipe_run(fe.h, fe.h, bbuf.ptr, nbytes, 1, L.SDR_DEVICE, y.ptr, 2 * n, L.SDR_DEVICE, C.byref(n_out)))
+        L.check(L.lib.sdr_pipe_run(fe.h, fe.h, bbuf.ptr, nbytes, 1, L.SDR_DEVICE_HELD, y.ptr, 2 * n, L.SDR_DEVICE, C.byref(n_out)))
     ms = timed(front, steps=4, warm=2)
     put("cfg4_front", "fused front end alone: u8 IQ -> convert -> decimate-by-8 -> fmDemod, one push", ms, n, 2.5, 32, L.lib.sdr_pipe_last_kernel(fe.h).decode())
     fe.close()
@@ -847,7 +860,7 @@ def run_configs(args, ctx, dec, sdr_b200, L, peak):
 
 
 def run_pipes_mode(args, ctx, dec, sdr_b200, L):
-    """device-resident Pipes mode, vector by vector: 8192-sample SDR_DEVICE vectors pushed through firDecimator by the native
+    """device-resident Pipes mode, vector by vector: 8192-sample device vectors pushed through firDecimator by the native
     loop (sdr_pipe_run), launch threshold = 1 / 8 / 256 output vectors (sdr_pipe_set_batch)"""
     n = 1 << min(args.log2n, 26)
     x = ctx.alloc(8 * n + 256)
@@ -855,26 +868,30 @@ def run_pipes_mode(args, ctx, dec, sdr_b200, L):
     ctx.synth_noise(x, 2 * n)
     res = {"vector": BUF, "samples": n, "unit": "Msamples/s"}
     n_out = C.c_longlong()
-    for batch in (0, 8, 256):
-        pipe = sdr_b200.pipeFirDecimator(dec, BUF)
-        L.check(L.lib.sdr_pipe_set_batch(pipe.h, batch * BUF))
+    for mem, tag in ((L.SDR_DEVICE_HELD, ""), (L.SDR_DEVICE, "_copied")):
+        for batch in (0, 8, 256):
+            pipe = sdr_b200.pipeFirDecimator(dec, BUF)
+            L.check(L.lib.sdr_pipe_set_batch(pipe.h, batch * BUF))
 
-        def run():
-            L.check(L.lib.sdr_pipe_run(pipe.h, pipe.h, x.ptr, BUF, n // BUF, L.SDR_DEVICE, y.ptr, n // FACTOR + BUF, L.SDR_DEVICE, C.byref(n_out)))
-        for _ in range(2):
-            run()
-        ctx.sync()
-        l0 = ctx.launches
-        t0 = time.perf_counter()
-        e0, e1 = sdr_b200.Event(ctx), sdr_b200.Event(ctx)
-        e0.record()
-        for _ in range(3):
-            run()
-        e1.record()
-        ms = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3) / 3
-        res[f"batch_{batch}"] = {"value": n / (ms * 1e-3) / 1e6, "ms": ms, "launches_per_pass": (ctx.launches - l0) / 3,
-                                 "input_vectors_per_launch": (n // BUF) / max(1.0, (ctx.launches - l0) / 3)}
-        pipe.close()
+            def run():
+                L.check(L.lib.sdr_pipe_run(pipe.h, pipe.h, x.ptr, BUF, n // BUF, mem, y.ptr, n // FACTOR + BUF, L.SDR_DEVICE, C.byref(n_out)))
+            for _ in range(2):
+                run()
+            ctx.sync()
+            l0 = ctx.launches
+            t0 = time.perf_counter()
+            e0, e1 = sdr_b200.Event(ctx), sdr_b200.Event(ctx)
+            e0.record()
+            for _ in range(3):
+                run()
+            e1.record()
+            ms = max(e0.elapsed_ms(e1), (time.perf_counter() - t0) * 1e3) / 3
+            res[f"batch_{batch}{tag}"] = {"value": n / (ms * 1e-3) / 1e6, "ms": ms, "launches_per_pass": (ctx.launches - l0) / 3,
+                                          "input_vectors_per_launch": (n // BUF) / max(1.0, (ctx.launches - l0) / 3)}
+            pipe.close()
+    res["note"] = ("batch_N: launch threshold of N output vectors (N = 0: as soon as one 8192-sample output vector completes = every 8 input "
+                   "vectors); default rows push SDR_DEVICE_HELD vectors (read in place, zero-copy), *_copied rows push SDR_DEVICE vectors "
+                   "(one device-to-device copy per vector into the stage, round 1's only mode)")
     x.free(); y.free()
     return res
 

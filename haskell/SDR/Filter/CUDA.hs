@@ -12,7 +12,10 @@ module SDR.Filter.CUDA (
     cudaFilterR, cudaFilterC, cudaFilterSymR,
     cudaDecimatorR, cudaDecimatorC, cudaDecimatorSymR,
     cudaResamplerR, cudaResamplerC,
-    cudaDecimatorOrFast
+    cudaDecimatorOrFast,
+    -- * Record handles for the device-resident stages of "SDR.Pipes.CUDA"
+    FilterH, DecimatorH, ResamplerH, Ctx, defaultCtx,
+    filterHandle, decimatorHandle, resamplerHandle
     ) where
 
 import           Control.Monad                (unless, when)
@@ -194,3 +197,37 @@ cudaResamplerR = mkCudaResampler False
 -- | 'SDR.Filter.fastResamplerC' (Filter.hs:497-502)
 cudaResamplerC :: Int -> Int -> [Float] -> IO (Resampler IO VS.Vector VS.MVector (Complex Float))
 cudaResamplerC = mkCudaResampler True
+
+-- Handles for "SDR.Pipes.CUDA" ---------------------------------------------------------------------------------------
+-- The device-resident stages (sdr_pipe_fir_decimator ...) take the plugin record by handle and keep referring to it,
+-- so they receive the ForeignPtr itself (the stage stores it: the record cannot be finalized before the stage).
+
+-- | the handle of a 'cudaFilterR' / 'cudaFilterC' / 'cudaFilterSymR' style record: complex data?, symmetric half taps?
+filterHandle :: Bool -> Bool -> [Float] -> IO (ForeignPtr FilterH)
+filterHandle cplx sym coeffs = do
+    ctx <- defaultCtx
+    h   <- alloca $ \pp -> do
+        withCoeffs coeffs $ \pc n ->
+            if sym then check (c_filterCreateSym ctx (if cplx then 1 else 0) pc n pp)
+                   else check (c_filterCreate ctx (if cplx then 1 else 0) pc n 1 pp)
+        peek pp
+    newForeignPtr p_filterDestroy h
+
+-- | the handle of a 'cudaDecimatorC' style record
+decimatorHandle :: Bool -> Int -> [Float] -> IO (ForeignPtr DecimatorH)
+decimatorHandle cplx factor coeffs = do
+    ctx <- defaultCtx
+    h   <- alloca $ \pp -> do
+        withCoeffs coeffs $ \pc n -> check (c_decimatorCreate ctx (if cplx then 1 else 0) (fromIntegral factor) pc n 1 pp)
+        peek pp
+    newForeignPtr p_decimatorDestroy h
+
+-- | the handle of a 'cudaResamplerR' style record
+resamplerHandle :: Bool -> Int -> Int -> [Float] -> IO (ForeignPtr ResamplerH)
+resamplerHandle cplx interpolation decimation coeffs = do
+    ctx <- defaultCtx
+    h   <- alloca $ \pp -> do
+        withCoeffs coeffs $ \pc n ->
+            check (c_resamplerCreate ctx (if cplx then 1 else 0) (fromIntegral interpolation) (fromIntegral decimation) pc n 1 pp)
+        peek pp
+    newForeignPtr p_resamplerDestroy h

@@ -57,8 +57,13 @@ enum {
 enum {
     SDR_HOST = 0,        /* any host memory; the call returns only when the library no longer needs the pointer */
     SDR_DEVICE = 1,      /* device memory of the handle's context; enqueue-only on the ctx stream             */
-    SDR_HOST_PINNED = 2  /* sdr_pipe_push / sdr_pipe_pop only: page-locked host memory the caller leaves untouched
+    SDR_HOST_PINNED = 2, /* sdr_pipe_push / sdr_pipe_pop only: page-locked host memory the caller leaves untouched
                             until sdr_pipe_sync -- enqueue-only, no staging copy, copies of adjacent vectors merge */
+    SDR_DEVICE_HELD = 3  /* sdr_pipe_push / sdr_pipe_run only: device memory the caller leaves untouched until sdr_pipe_sync
+                            -- ZERO-COPY: FIR stages read the vector in place (vectors adjacent in memory form one run that
+                            the next launch reads together with the stage's carried tail); only the few samples a launch
+                            leaves over are copied into the stage.  This is the Pipes zero-copy contract on the device:
+                            a yielded vector is immutable and the stage may keep referring to it (Filter.hs:519-521) */
 };
 
 /* arithmetic mode of the FIR kernels */
@@ -286,6 +291,11 @@ int sdr_pipe_fm_frontend(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **p)
  * u8 IQ bytes (n = byte count, even), yields are vectors of block_size_out COMPLEX samples.  Same stream, bit for bit, as
  * the two stages connected one after the other; the host link carries 2 B per input sample instead of 8. */
 int sdr_pipe_u8_decimator(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **p);
+/* `firResampler r block_size_resampler >-> firFilter f block_size_out >-> P.map (VG.map (* scale))` (fm.hs:38-40) as ONE
+ * fused stage: real vectors in, vectors of block_size_out scaled filter outputs out; the resampled stream never touches
+ * HBM.  Same stream, bit for bit, as the three stages connected one after the other (the filter only ever sees whole
+ * block_size_resampler vectors of resampled samples, as it does behind the un-fused resampler stage). */
+int sdr_pipe_fm_lowrate(sdr_resampler_t *r, int block_size_resampler, sdr_filter_t *f, int block_size_out, float scale, sdr_pipe_t **p);
 const char *sdr_pipe_last_kernel(const sdr_pipe_t *p);
 int sdr_pipe_convert_u8(sdr_ctx_t *ctx, sdr_pipe_t **p); /* P.map interleavedIQUnsignedByteToFloat (Util.hs:104) */
 int sdr_pipe_scale(sdr_ctx_t *ctx, float factor, sdr_pipe_t **p);                   /* P.map (VG.map (* k)) fm.hs:40 */

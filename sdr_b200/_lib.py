@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SDR_B200_LIB_PATH") or os.path.join(_HERE, "lib", "libsdr_b200.so")
 
 SDR_OK, SDR_EINVAL, SDR_EPRECOND, SDR_ECUDA, SDR_ENODEVICE, SDR_ENOMEM, SDR_ENCCL, SDR_EAGAIN = range(8)
-SDR_HOST, SDR_DEVICE, SDR_HOST_PINNED = 0, 1, 2
+SDR_HOST, SDR_DEVICE, SDR_HOST_PINNED, SDR_DEVICE_HELD = 0, 1, 2, 3
 SDR_ARITH_FAST, SDR_ARITH_EXACT = 0, 1
 V_SCALAR, V_SSE, V_AVX, V_SSE2, V_AVX2, V_SSESYM, V_AVXSYM = range(7)
 COMM_ID_BYTES = 128
@@ -152,6 +152,7 @@ _sig("sdr_pipe_fir_resampler", _P, _I, c_void_pp)
 _sig("sdr_pipe_fm_demod", _P, c_void_pp)
 _sig("sdr_pipe_fm_frontend", _P, _I, c_void_pp)
 _sig("sdr_pipe_u8_decimator", _P, _I, c_void_pp)
+_sig("sdr_pipe_fm_lowrate", _P, _I, _P, _I, _F, c_void_pp)
 lib.sdr_pipe_last_kernel.restype = C.c_char_p
 lib.sdr_pipe_last_kernel.argtypes = [C.c_void_p]
 _sig("sdr_pipe_convert_u8", _P, c_void_pp)

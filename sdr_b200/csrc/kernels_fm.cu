@@ -76,7 +76,8 @@ __device__ __forceinline__ float2 unpack2f(u64 v) {
 // (fm.hs:34-36) alone: `out` then receives the decimated COMPLEX samples (8 B each), bnd / carry_out are unused.
 template <int T, int D, int R, int NW, bool SYM, bool DEMOD = true>
 __global__ void __launch_bounds__(32 * NW, 1)
-k_fm_front_ring(const uint8_t *__restrict__ in, long long n_chunks, float *__restrict__ out, long long num,
+k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_t *__restrict__ in_b, long long n_chunks,
+                float *__restrict__ out, long long num,
                 float2 *__restrict__ bnd, float2 *__restrict__ carry_out, const float *__restrict__ taps, long long n_sub) {
     typedef FmCfg<T, D, R, NW> C;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -96,24 +97,28 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long n_chunks, float *__res
     }
     __syncthreads();
 
-    // chunk c (16 B = 8 IQ pairs) of a sub-tile lands in segment c / 8 at offset (c % 8) * 16
+    // chunk c (16 B = 8 IQ pairs) of a sub-tile lands in segment c / 8 at offset (c % 8) * 16.  The byte stream is `in`
+    // (a_chunks chunks: the stage's carried tail) followed by `in_b` (up to n_chunks in all: vectors read in place from
+    // the caller's memory); chunks past n_chunks are zero-filled.
+    auto chunk_src = [&](long long g) -> const unsigned char * {
+        return g < a_chunks ? in + g * 16 : in_b + (g - a_chunks) * 16;
+    };
     auto issue_fill = [&](int u) {
         const int slot = u % C::NS;
-        const int nchunk = (u == cnt) ? C::HALO_SEGS * R : 32 * R;   // halo-only fill: the first two segments
+        const int nchunk = (u == cnt) ? C::HALO_SEGS * R : 32 * R;   // halo-only fill: the first segments
         const long long chunk0 = (s0 + u) * (long long)(32 * R);
-        const unsigned char *src = in + chunk0 * 16;
         const uint32_t dst = ring + slot * C::SLOT_BYTES;
 #pragma unroll
         for (int i = 0; i < R; i++) {
             const int c = i * 32 + lane;
             if (c < nchunk) {
                 const bool ok = chunk0 + c < n_chunks;
-                cp_async16(dst + (c >> 3) * C::SEG_STRIDE + (c & 7) * 16, ok ? src + c * 16 : in, ok ? 16u : 0u);
+                cp_async16(dst + (c >> 3) * C::SEG_STRIDE + (c & 7) * 16, ok ? chunk_src(chunk0 + c) : in, ok ? 16u : 0u);
             }
         }
         if (slot == 0 && lane < C::HALO_SEGS * R) {   // mirror of slot 0's head behind the last slot
             const bool ok = chunk0 + lane < n_chunks;
-            cp_async16(ring + C::NS * C::SLOT_BYTES + (lane >> 3) * C::SEG_STRIDE + (lane & 7) * 16, ok ? src + lane * 16 : in,
+            cp_async16(ring + C::NS * C::SLOT_BYTES + (lane >> 3) * C::SEG_STRIDE + (lane & 7) * 16, ok ? chunk_src(chunk0 + lane) : in,
                        ok ? 16u : 0u);
         }
         cp_async_arrive(bar_full + 8 * slot);
@@ -221,12 +226,12 @@ __global__ void __launch_bounds__(256) k_fm_front_fixup(float *__restrict__ out,
 
 // One launch of the fused kernel for tap capacity TK (the record's taps zero-padded up to it), D = 8.
 template <int TK, int NW, bool SYM, bool DEMOD>
-static int launch_front_inst(Ctx *c, const float *d_taps, const uint8_t *d_in, long long n_samples, float *d_out, long long num,
-                             float2 *d_bnd, float2 *d_carry_out, long long n_sub) {
+static int launch_front_inst(Ctx *c, const float *d_taps, const uint8_t *d_in, long long n_samples, const uint8_t *d_in_b,
+                             long long a_samples, float *d_out, long long num, float2 *d_bnd, float2 *d_carry_out, long long n_sub) {
     typedef FmCfg<TK, 8, 8, NW> C;
     SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<TK, 8, 8, NW, SYM, DEMOD>), C::SMEM_BYTES));
     int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
-    k_fm_front_ring<TK, 8, 8, NW, SYM, DEMOD><<<grid, 32 * NW, C::SMEM_BYTES, c->s()>>>(d_in, n_samples / 8, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
+    k_fm_front_ring<TK, 8, 8, NW, SYM, DEMOD><<<grid, 32 * NW, C::SMEM_BYTES, c->s()>>>(d_in, a_samples / 8, d_in_b, n_samples / 8, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     return SDR_OK;
@@ -237,34 +242,36 @@ static int launch_front_inst(Ctx *c, const float *d_taps, const uint8_t *d_in, l
 // 16 warps.  `label` receives the kernel's name without its prefix.
 template <bool DEMOD>
 static int launch_front_any(Ctx *c, int taps_stored, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
-                            float *d_out, long long num, float2 *d_bnd, float2 *d_carry_out, long long n_sub, const char **label) {
+                            const uint8_t *d_in_b, long long a_samples, float *d_out, long long num, float2 *d_bnd, float2 *d_carry_out,
+                            long long n_sub, const char **label) {
     if (taps_stored > 64) {
-        if (symmetric && taps_stored == 128) { *label = "<128,8,8,sym,16w>"; return launch_front_inst<128, 16, true, DEMOD>(c, d_taps, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub); }
+        if (symmetric && taps_stored == 128) { *label = "<128,8,8,sym,16w>"; return launch_front_inst<128, 16, true, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub); }
         *label = "<128,8,8>";
-        return launch_front_inst<128, 8, false, DEMOD>(c, d_taps, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub);
+        return launch_front_inst<128, 8, false, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub);
     }
-    if (taps_stored > 32) { *label = "<64,8,8,16w>"; return launch_front_inst<64, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub); }
+    if (taps_stored > 32) { *label = "<64,8,8,16w>"; return launch_front_inst<64, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub); }
     *label = "<32,8,8,16w>";
-    return launch_front_inst<32, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub);
+    return launch_front_inst<32, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub);
 }
 
 // Fused convert + decimate + demod of outputs [0, num) of a byte stream holding n_samples IQ pairs.  d_carry: previous
 // stream sample (re, im) on the device, read by the fix-up; d_carry_out receives the last decimated complex output;
 // d_bnd: scratch of 2 complex per sub-tile (ceil(num / 256) sub-tiles).  *done = num when the shape has a tuned kernel.
 // T = the record's stored tap count (d_taps zero-padded to >= 128 floats).
-int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
-                    float *d_out, long long num, float2 *d_bnd, long long bnd_capacity_subtiles, const float2 *d_carry,
-                    float2 *d_carry_out, long long *done, const char **name) {
+int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long a_samples,
+                    const uint8_t *d_in_b, long long n_samples, float *d_out, long long num, float2 *d_bnd,
+                    long long bnd_capacity_subtiles, const float2 *d_carry, float2 *d_carry_out, long long *done, const char **name) {
     *done = 0;
     *name = "unfused";
     if (T > 128 || D != 8 || num <= 0) return SDR_OK;
     if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 3) != 0) return SDR_OK;
+    if (a_samples < n_samples && ((a_samples & 7) != 0 || (((uintptr_t)d_in_b) & 15) != 0)) return SDR_OK;   // segment boundary on a chunk
     if ((num - 1) * D + T > n_samples) return set_error(SDR_EINVAL, "launch_fm_front: %lld outputs need more than %lld samples", num, n_samples);
     const long long n_sub = (num + 255) / 256;
     if (bnd_capacity_subtiles < n_sub) return set_error(SDR_EINVAL, "launch_fm_front: boundary scratch too small");
     SDR_TRY(c->bind());
     const char *label = "";
-    SDR_TRY(launch_front_any<true>(c, T, d_taps, symmetric, d_in, n_samples, d_out, num, d_bnd, d_carry_out, n_sub, &label));
+    SDR_TRY(launch_front_any<true>(c, T, d_taps, symmetric, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub, &label));
     static thread_local char nm[64];
     snprintf(nm, sizeof(nm), "fm_front_ring%s", label);
     *name = nm;
@@ -279,17 +286,18 @@ int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, c
 
 // Fused convert + decimate (no demodulation) of outputs [0, num) of a byte stream holding n_samples IQ pairs: complex
 // outputs.  *done = num when the shape has a tuned kernel, else 0 (the caller runs the two stages one after the other).
-int launch_dec_u8(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
-                  float *d_out, long long num, long long *done, const char **name) {
+int launch_dec_u8(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long a_samples,
+                  const uint8_t *d_in_b, long long n_samples, float *d_out, long long num, long long *done, const char **name) {
     *done = 0;
     *name = "unfused";
     if (T > 128 || D != 8 || num <= 0) return SDR_OK;
     if ((((uintptr_t)d_in) & 15) != 0 || (((uintptr_t)d_out) & 7) != 0) return SDR_OK;
+    if (a_samples < n_samples && ((a_samples & 7) != 0 || (((uintptr_t)d_in_b) & 15) != 0)) return SDR_OK;
     if ((num - 1) * D + T > n_samples) return set_error(SDR_EINVAL, "launch_dec_u8: %lld outputs need more than %lld samples", num, n_samples);
     const long long n_sub = (num + 255) / 256;
     SDR_TRY(c->bind());
     const char *label = "";
-    SDR_TRY(launch_front_any<false>(c, T, d_taps, symmetric, d_in, n_samples, d_out, num, nullptr, nullptr, n_sub, &label));
+    SDR_TRY(launch_front_any<false>(c, T, d_taps, symmetric, d_in, n_samples, d_in_b, a_samples, d_out, num, nullptr, nullptr, n_sub, &label));
     static thread_local char nm[64];
     snprintf(nm, sizeof(nm), "dec_u8_ring%s", label);
     *name = nm;

@@ -52,8 +52,11 @@ template <bool CPLX, int T, int D, int R, int S>
 __global__ void __launch_bounds__(256, 1)
 k_fir_ring(const void *__restrict__ in_v, void *__restrict__ out_v, const float *__restrict__ taps, long long n_slots) {
     typedef FirRCfg<CPLX, T, D, R, S> C;
-    const bool vec16 = (reinterpret_cast<uintptr_t>(out_v) & 15) == 0 && (R * C::EB) % 16 == 0;
-    const bool vec8 = (reinterpret_cast<uintptr_t>(out_v) & 7) == 0 && (R * C::EB) % 8 == 0;
+    // widest store a lane's R outputs allow (compile time) and the output pointer permits (run time): ONE vector variant
+    // plus the scalar one per instantiation, so the compiler clones the unrolled loop body only twice
+    constexpr bool CAN16 = (R * C::EB) % 16 == 0;
+    constexpr bool CAN8 = !CAN16 && (R * C::EB) % 8 == 0;
+    const bool vec_store = (reinterpret_cast<uintptr_t>(out_v) & (CAN16 ? 15 : 7)) == 0 && (CAN16 || CAN8);
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long q = n_slots / gridDim.x, rem = n_slots % gridDim.x;
@@ -91,7 +94,7 @@ k_fir_ring(const void *__restrict__ in_v, void *__restrict__ out_v, const float 
                     }
                 }
                 u64 *os = reinterpret_cast<u64 *>(out_v) + o0;
-                if (vec16) {
+                if (CAN16 && vec_store) {
                     ulonglong2 *o = reinterpret_cast<ulonglong2 *>(os);
 #pragma unroll
                     for (int r = 0; r + 1 < R; r += 2) o[r / 2] = make_ulonglong2(acc[r], acc[r + 1]);
@@ -117,11 +120,11 @@ k_fir_ring(const void *__restrict__ in_v, void *__restrict__ out_v, const float 
                     }
                 }
                 float *os = reinterpret_cast<float *>(out_v) + o0;
-                if (vec16) {
+                if (CAN16 && vec_store) {
                     float4 *o = reinterpret_cast<float4 *>(os);
 #pragma unroll
                     for (int r = 0; r + 3 < R; r += 4) o[r / 4] = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
-                } else if (vec8) {
+                } else if (CAN8 && vec_store) {
                     float2 *o = reinterpret_cast<float2 *>(os);
 #pragma unroll
                     for (int r = 0; r + 1 < R; r += 2) o[r / 2] = make_float2(acc[r], acc[r + 1]);

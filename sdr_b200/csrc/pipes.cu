@@ -100,7 +100,8 @@ static void trace_dump() {
     trace_log().clear();
 }
 
-enum { P_FILTER, P_DECIM, P_RESAMP, P_FMDEMOD, P_CONVERT, P_SCALE, P_FMFRONT, P_DCBLOCK, P_U8DECIM };
+enum { P_FILTER, P_DECIM, P_RESAMP, P_FMDEMOD, P_CONVERT, P_SCALE, P_FMFRONT, P_DCBLOCK, P_U8DECIM, P_FMLOW };
+enum { MEM_FWD = 100 };   // internal: a connected upstream stage hands over its FIFO region, read in place
 
 }  // namespace sdr
 
@@ -141,11 +142,17 @@ struct sdr_pipe {
     const char *pend_src = nullptr;
     char *pend_dst = nullptr;
     size_t pend_bytes = 0;
+    // zero-copy input: a run of device vectors (SDR_DEVICE_HELD pushes adjacent in memory, or the FIFO region a connected
+    // upstream stage hands over) that logically FOLLOWS the live region of `in` and is read in place by the next launch
+    const char *ext_p = nullptr;
+    size_t ext_bytes = 0;
+    long long block_r = 0;            // fused low-rate stage: the resampler stage's own vector length (its yields gate the filter)
 };
 
 namespace sdr {
 
-static bool is_fir_kind(int k) { return k == P_FILTER || k == P_DECIM || k == P_RESAMP || k == P_FMFRONT || k == P_U8DECIM; }
+static bool is_fir_kind(int k) { return k == P_FILTER || k == P_DECIM || k == P_RESAMP || k == P_FMFRONT || k == P_U8DECIM || k == P_FMLOW; }
+static bool is_resamp_kind(int k) { return k == P_RESAMP || k == P_FMLOW; }
 static bool is_byte_fed(int k) { return k == P_FMFRONT || k == P_U8DECIM; }
 
 static int fifo_writable(sdr_pipe *p) {
@@ -162,6 +169,39 @@ static int flush_pending(sdr_pipe *p) {
     return SDR_OK;
 }
 
+static long long in_elems(const sdr_pipe *p) { return (long long)((p->in.size() + p->ext_bytes) / p->in_eb); }
+// the resident input stream as (carried tail, in-place run); one segment when there is no tail
+static Seg2 input_seg(const sdr_pipe *p) {
+    Seg2 s = {p->in.p + p->in.rd, (long long)(p->in.size() / p->in_eb), p->ext_p, (long long)(p->ext_bytes / p->in_eb)};
+    if (s.na == 0 && s.nb > 0) { s.a = s.b; s.na = s.nb; s.b = nullptr; s.nb = 0; }
+    return s;
+}
+static Seg2 seg_advance(Seg2 s, long long first, size_t eb) {
+    if (first >= s.na) { s.a = (const char *)s.b + (size_t)(first - s.na) * eb; s.na = s.nb - (first - s.na); s.b = nullptr; s.nb = 0;
+                         if (s.na < 0) s.na = 0; }
+    else               { s.a = (const char *)s.a + (size_t)first * eb; s.na -= first; }
+    return s;
+}
+// copy what is left of the in-place run behind the carried tail: afterwards the stage references only its own memory
+static int materialize_ext(sdr_pipe *p) {
+    if (!p->ext_bytes) return SDR_OK;
+    SDR_TRY(flush_pending(p));
+    SDR_TRY(p->in.reserve(p->ext_bytes));
+    SDR_CUDA(cudaMemcpyAsync(p->in.p + p->in.wr, p->ext_p, p->ext_bytes, cudaMemcpyDeviceToDevice, p->ctx->stream));
+    p->in.wr += p->ext_bytes;
+    p->ext_p = nullptr; p->ext_bytes = 0;
+    return SDR_OK;
+}
+// drop `bytes` from the front of the resident stream (tail first, then the in-place run)
+static void consume_input(sdr_pipe *p, size_t bytes) {
+    const size_t live = p->in.size();
+    if (bytes < live) { p->in.rd += bytes; return; }
+    p->in.rd = p->in.wr = 0;
+    const size_t rest = bytes - live;
+    p->ext_p += rest; p->ext_bytes -= rest;
+    if (p->ext_bytes == 0) p->ext_p = nullptr;
+}
+
 static int pipe_push_dev(sdr_pipe *p, const void *d_src, long long n);
 static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, long long n_vecs = 1);
 
@@ -173,7 +213,7 @@ static int forward(sdr_pipe *p) {
         long long nb = have / p->block_out;
         if (nb > 0 && is_fir_kind(p->downstream->kind)) {
             // a FIR stage only sees the flat stream: hand it all complete vectors as one contiguous push
-            SDR_TRY(pipe_push_dev(p->downstream, p->fifo.p + p->fifo.rd, nb * p->block_out));
+            SDR_TRY(pipe_push_any(p->downstream, p->fifo.p + p->fifo.rd, nb * p->block_out, MEM_FWD));
             p->fifo.consume((size_t)(nb * p->block_out) * p->out_eb);
         } else if (nb > 0) {
             // element-wise stages yield one vector per awaited vector: one launch over all of them, but the vector
@@ -188,10 +228,10 @@ static int forward(sdr_pipe *p) {
             long long total = 0, shortest = p->vec_lens.front();
             for (long long n : p->vec_lens) { total += n; if (n < shortest) shortest = n; }
             sdr_pipe *d = p->downstream;
-            long long need = (d->kind == P_RESAMP) ? (d->res->T + d->res->L - 1) / d->res->L : d->fir->T;
+            long long need = is_resamp_kind(d->kind) ? (d->res->T + d->res->L - 1) / d->res->L : d->fir->T;
             if (shortest >= need) {
                 p->vec_lens.clear();
-                SDR_TRY(pipe_push_dev(d, p->fifo.p + p->fifo.rd, total));
+                SDR_TRY(pipe_push_any(d, p->fifo.p + p->fifo.rd, total, MEM_FWD));
                 p->fifo.consume((size_t)total * p->out_eb);
                 return SDR_OK;
             }
@@ -199,7 +239,7 @@ static int forward(sdr_pipe *p) {
         while (!p->vec_lens.empty()) {
             long long n = p->vec_lens.front();
             p->vec_lens.pop_front();
-            SDR_TRY(pipe_push_dev(p->downstream, p->fifo.p + p->fifo.rd, n));
+            SDR_TRY(pipe_push_any(p->downstream, p->fifo.p + p->fifo.rd, n, is_fir_kind(p->downstream->kind) ? (int)MEM_FWD : (int)SDR_DEVICE));
             p->fifo.consume((size_t)n * p->out_eb);
         }
     }
@@ -230,7 +270,7 @@ static int fm_unfused(sdr_pipe *p, long long first, long long n, const float *d_
 // sub-tile and unaligned FIFO cursor included); shapes without a tuned kernel run the three stages un-fused.
 static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     FirRec &f = *p->fir;
-    const long long have = (long long)(p->in.size() / 2);   // IQ pairs resident
+    const long long have = in_elems(p) / 2;   // IQ pairs resident (carried tail + in-place run)
     long long count = (have >= f.T) ? (have - f.T) / f.D + 1 : 0;
     if (!(count > 0 && fifo_have + count >= p->block_out && fifo_have + count >= batch)) return SDR_OK;
     SDR_TRY(flush_pending(p));
@@ -244,10 +284,13 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     float *carry_in = p->d_last + 2 * p->last_sel, *carry_out = p->d_last + 2 * (p->last_sel ^ 1);
     long long done = 0;
     const char *name = nullptr;
-    SDR_TRY(launch_fm_front(p->ctx, f.T, f.D, f.d_taps, f.symmetric, (const uint8_t *)(p->in.p + p->in.rd), have, out, count, (float2 *)p->bnd.p,
-                            (long long)(p->bnd.cap / 16), (const float2 *)carry_in, (float2 *)carry_out, &done, &name));
+    Seg2 seg = input_seg(p);   // element = byte
+    SDR_TRY(launch_fm_front(p->ctx, f.T, f.D, f.d_taps, f.symmetric, (const uint8_t *)seg.a, seg.nb ? seg.na / 2 : have, (const uint8_t *)seg.b,
+                            have, out, count, (float2 *)p->bnd.p, (long long)(p->bnd.cap / 16), (const float2 *)carry_in, (float2 *)carry_out,
+                            &done, &name));
     p->last_kernel = name;
     if (done < count) {
+        SDR_TRY(materialize_ext(p));   // the un-fused stages read one contiguous segment
         const float *last = nullptr;
         SDR_TRY(fm_unfused(p, 0, count, carry_in, out, 1, &last));
         SDR_CUDA(cudaMemcpyAsync(carry_out, last, 8, cudaMemcpyDeviceToDevice, p->ctx->stream));
@@ -257,8 +300,9 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     {
         const long long adv = count * f.D < have ? count * f.D : have;
         p->skip += 2 * (count * f.D - adv);
-        p->in.rd += (size_t)adv * 2;
+        consume_input(p, (size_t)adv * 2);
     }
+    SDR_TRY(materialize_ext(p));   // the short tail moves behind the stage's own buffer; the caller's vectors are released
     if (p->in.size() <= (1u << 16) && p->in.rd > p->in.cap / 4) SDR_TRY(p->in.realign(0));
     return SDR_OK;
 }
@@ -267,7 +311,7 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
 // without a tuned kernel convert into scratch and run the decimator record on it.
 static int process_u8_decim(sdr_pipe *p, long long fifo_have, long long batch) {
     FirRec &f = *p->fir;
-    const long long have = (long long)(p->in.size() / 2);   // IQ pairs resident
+    const long long have = in_elems(p) / 2;   // IQ pairs resident
     long long count = (have >= f.T) ? (have - f.T) / f.D + 1 : 0;
     if (!(count > 0 && fifo_have + count >= p->block_out && fifo_have + count >= batch)) return SDR_OK;
     SDR_TRY(flush_pending(p));
@@ -277,29 +321,76 @@ static int process_u8_decim(sdr_pipe *p, long long fifo_have, long long batch) {
     float *out = (float *)(p->fifo.p + p->fifo.wr);
     long long done = 0;
     const char *name = nullptr;
-    SDR_TRY(launch_dec_u8(p->ctx, f.T, f.D, f.d_taps, f.symmetric, (const uint8_t *)(p->in.p + p->in.rd), have, out, count, &done, &name));
+    Seg2 seg = input_seg(p);
+    SDR_TRY(launch_dec_u8(p->ctx, f.T, f.D, f.d_taps, f.symmetric, (const uint8_t *)seg.a, seg.nb ? seg.na / 2 : have, (const uint8_t *)seg.b, have,
+                          out, count, &done, &name));
     p->last_kernel = name;
     if (done < count) {
+        SDR_TRY(materialize_ext(p));
         const long long n_s = (count - 1) * f.D + f.T;
         p->scratch_x.rd = p->scratch_x.wr = 0;
         SDR_TRY(p->scratch_x.reserve((size_t)n_s * 8 + 256));
         SDR_TRY(launch_convert_u8(p->ctx, (const uint8_t *)(p->in.p + p->in.rd), (float *)p->scratch_x.p, 2 * n_s));
-        Seg2 seg = {p->scratch_x.p, n_s, nullptr, 0};
-        SDR_TRY(f.run(seg, 0, out, count, false));
+        Seg2 one = {p->scratch_x.p, n_s, nullptr, 0};
+        SDR_TRY(f.run(one, 0, out, count, false));
     }
     p->fifo.wr += (size_t)count * 8;
     {
         const long long adv = count * f.D < have ? count * f.D : have;
         p->skip += 2 * (count * f.D - adv);
-        p->in.rd += (size_t)adv * 2;
+        consume_input(p, (size_t)adv * 2);
     }
+    SDR_TRY(materialize_ext(p));
+    if (p->in.size() <= (1u << 16) && p->in.rd > p->in.cap / 4) SDR_TRY(p->in.realign(0));
+    return SDR_OK;
+}
+
+// firResampler >-> firFilter >-> P.map (* k) as one stage (fm.hs:38-40).  The resampler stage of the un-fused chain only
+// yields whole vectors of block_r elements, so the filter sees R_avail = floor(R_total / block_r) * block_r resampled
+// samples and can produce R_avail - numCoeffsF + 1 outputs: the fused stage yields exactly those.
+static int process_fm_low(sdr_pipe *p, long long fifo_have, long long batch) {
+    ResRec &r = *p->res;
+    FirRec &f = *p->fir;
+    const long long r_total = (p->n_total * r.L >= r.T) ? (p->n_total * r.L - r.T) / r.M + 1 : 0;
+    const long long r_avail = (r_total / p->block_r) * p->block_r;
+    const long long z_total = r_avail >= f.T ? r_avail - f.T + 1 : 0;
+    const long long count = z_total - p->k_next;
+    if (!(count > 0 && fifo_have + count >= p->block_out && fifo_have + count >= batch)) return SDR_OK;
+    SDR_TRY(flush_pending(p));
+    TraceScope tr("fm_lowrate", p->ctx, count);
+    SDR_TRY(fifo_writable(p));
+    SDR_TRY(p->fifo.reserve((size_t)count * 4));
+    float *out = (float *)(p->fifo.p + p->fifo.wr);
+    const long long i_k = (p->k_next * r.M + r.L - 1) / r.L;   // first sample of resampler output k_next
+    Seg2 seg = seg_advance(input_seg(p), i_k - p->pos, 4);
+    long long done = 0;
+    const char *name = nullptr;
+    SDR_TRY(launch_fm_lowrate(p->ctx, r.L, r.M, r.n_taps, r.d_plain, f.T, f.d_taps, p->scale_k, seg, p->k_next, out, count, &done, &name));
+    p->last_kernel = name;
+    if (done < count) {   // no fused kernel for the shape: the three stages one after the other through scratch
+        const long long nr = count + f.T - 1;
+        p->scratch_x.rd = p->scratch_x.wr = 0; p->scratch_y.rd = p->scratch_y.wr = 0;
+        SDR_TRY(p->scratch_x.reserve((size_t)nr * 4 + 256));
+        SDR_TRY(p->scratch_y.reserve((size_t)count * 4 + 256));
+        SDR_TRY(r.run(seg, 0, (int)(p->k_next % r.ng), p->scratch_x.p, nr, false));
+        Seg2 one = {p->scratch_x.p, nr, nullptr, 0};
+        SDR_TRY(f.run(one, 0, p->scratch_y.p, count, false));
+        SDR_TRY(launch_scale(p->ctx, p->scale_k, (const float *)p->scratch_y.p, out, count));
+    }
+    p->fifo.wr += (size_t)count * 4;
+    p->k_next += count;
+    long long new_pos = (p->k_next * r.M + r.L - 1) / r.L;
+    if (new_pos > p->n_total) new_pos = p->n_total;
+    consume_input(p, (size_t)(new_pos - p->pos) * 4);
+    p->pos = new_pos;
+    SDR_TRY(materialize_ext(p));
     if (p->in.size() <= (1u << 16) && p->in.rd > p->in.cap / 4) SDR_TRY(p->in.realign(0));
     return SDR_OK;
 }
 
 // run whatever the stream now allows (FIR kinds); data already appended to p->in
 static int process_fir(sdr_pipe *p, bool force = false) {
-    long long have = (long long)(p->in.size() / p->in_eb);
+    long long have = in_elems(p);
     const long long fifo_have = (long long)(p->fifo.size() / p->out_eb);
     const long long batch = (force || p->batch_min < p->block_out) ? p->block_out : p->batch_min;
     if (p->kind == P_RESAMP) {
@@ -314,14 +405,14 @@ static int process_fir(sdr_pipe *p, bool force = false) {
             long long i_k = (p->k_next * r.M + r.L - 1) / r.L;   // ceil(k M / L): first sample of output k
             SDR_TRY(fifo_writable(p));
             SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
-            Seg2 seg = {p->in.p + p->in.rd, have, nullptr, 0};
-            SDR_TRY(r.run(seg, i_k - p->pos, (int)(p->k_next % r.ng), p->fifo.p + p->fifo.wr, count, false));
+            SDR_TRY(r.run(input_seg(p), i_k - p->pos, (int)(p->k_next % r.ng), p->fifo.p + p->fifo.wr, count, false));
             p->fifo.wr += (size_t)count * p->out_eb;
             p->k_next = total_out;
             long long new_pos = (p->k_next * r.M + r.L - 1) / r.L;
             if (new_pos > p->n_total) new_pos = p->n_total;
-            p->in.rd += (size_t)(new_pos - p->pos) * p->in_eb;
+            consume_input(p, (size_t)(new_pos - p->pos) * p->in_eb);
             p->pos = new_pos;
+            SDR_TRY(materialize_ext(p));
             if (!r.cplx && p->in.size() <= (1u << 16)) {
                 // the tuned kernel starts at the next cycle boundary (output index multiple of ng) with a 16-byte
                 // aligned window: park the short tail so that this start lands on a 16-byte boundary
@@ -334,6 +425,7 @@ static int process_fir(sdr_pipe *p, bool force = false) {
     }
     if (p->kind == P_FMFRONT) return process_fm_front(p, fifo_have, batch);
     if (p->kind == P_U8DECIM) return process_u8_decim(p, fifo_have, batch);
+    if (p->kind == P_FMLOW) return process_fm_low(p, fifo_have, batch);
     FirRec &f = *p->fir;
     long long count = (have >= f.T) ? (have - f.T) / f.D + 1 : 0;
     if (count > 0 && fifo_have + count >= p->block_out && (fifo_have + count >= batch)) {
@@ -341,14 +433,14 @@ static int process_fir(sdr_pipe *p, bool force = false) {
         TraceScope tr(p->kind == P_FILTER ? "filter" : "decimator", p->ctx, count);
         SDR_TRY(fifo_writable(p));
         SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
-        Seg2 seg = {p->in.p + p->in.rd, have, nullptr, 0};
-        SDR_TRY(f.run(seg, 0, p->fifo.p + p->fifo.wr, count, false));
+        SDR_TRY(f.run(input_seg(p), 0, p->fifo.p + p->fifo.wr, count, false));
         p->fifo.wr += (size_t)count * p->out_eb;
         {
             const long long adv = count * f.D < have ? count * f.D : have;
             p->skip += count * f.D - adv;
-            p->in.rd += (size_t)adv * p->in_eb;
+            consume_input(p, (size_t)adv * p->in_eb);
         }
+        SDR_TRY(materialize_ext(p));
         // park the short tail at the front right after a launch: keeps the tuned kernels' 16-byte alignment and means
         // the buffer never has to slide while it holds a half-collected batch
         if (p->in.size() <= (1u << 16) && ((p->in.rd & 15) || p->in.rd > p->in.cap / 4)) SDR_TRY(p->in.realign(0));
@@ -389,7 +481,7 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, lon
     TraceScope tr_push(trace_mode() == 1 ? "push(total)" : nullptr, p->ctx, n);
     if (is_fir_kind(p->kind)) {
         // the reference asserts every awaited vector holds at least numCoeffs samples (Filter.hs:544,586,691)
-        long long need = (p->kind == P_RESAMP) ? (p->res->T + p->res->L - 1) / p->res->L : p->fir->T;
+        long long need = is_resamp_kind(p->kind) ? (p->res->T + p->res->L - 1) / p->res->L : p->fir->T;
         if (is_byte_fed(p->kind)) {
             if (n & 1) return set_error(SDR_EINVAL, "u8 IQ stage: odd byte count %lld (interleaved I/Q pairs expected)", n);
             need *= 2;
@@ -402,6 +494,18 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, lon
             src = (const char *)src + (size_t)d * p->in_eb; n -= d; p->skip -= d;
             if (n == 0) return SDR_OK;
         }
+        if (mem == SDR_DEVICE_HELD || mem == MEM_FWD) {
+            // zero-copy: the vector is read in place by the next launch.  Vectors adjacent in memory extend the run; a
+            // vector somewhere else first moves the run collected so far behind the stage's own buffer.
+            SDR_TRY(flush_pending(p));
+            const size_t bytes = (size_t)n * p->in_eb;
+            if (p->ext_bytes && p->ext_p + p->ext_bytes == (const char *)src) p->ext_bytes += bytes;
+            else { SDR_TRY(materialize_ext(p)); p->ext_p = (const char *)src; p->ext_bytes = bytes; }
+            SDR_TRY(process_fir(p));
+            if (mem == MEM_FWD) SDR_TRY(materialize_ext(p));   // the upstream stage is about to reuse its FIFO
+            return forward(p);
+        }
+        SDR_TRY(materialize_ext(p));   // keeps the stream in order when held and copied pushes are mixed
         if (p->in.wr + (size_t)n * p->in_eb > p->in.cap) SDR_TRY(flush_pending(p));   // the buffer is about to move
         SDR_TRY(p->in.reserve((size_t)n * p->in_eb));
         SDR_TRY(fetch(p, p->in.p + p->in.wr, src, (size_t)n * p->in_eb, mem));
@@ -409,7 +513,8 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, lon
         SDR_TRY(process_fir(p));
         return forward(p);
     }
-    // element-wise kinds: one output vector per input vector
+    // element-wise kinds: one output vector per input vector (always read in place when the vector is on the device)
+    if (mem == SDR_DEVICE_HELD || mem == MEM_FWD) mem = SDR_DEVICE;
     long long n_out = n;
     const void *d_src = src;
     if (mem != SDR_DEVICE) {
@@ -485,6 +590,19 @@ int sdr_pipe_fm_frontend(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **ou
     SDR_CUDA(cudaMemsetAsync(p->d_last, 0, 16, p->ctx->stream));
     return SDR_OK;
 }
+int sdr_pipe_fm_lowrate(sdr_resampler_t *r, int block_size_resampler, sdr_filter_t *f, int block_size_out, float scale, sdr_pipe_t **out) {
+    if (!r || !f || block_size_resampler <= 0 || block_size_out <= 0) return set_error(SDR_EINVAL, "sdr_pipe_fm_lowrate: bad argument");
+    if (r->r.cplx || f->r.cplx) return set_error(SDR_EINVAL, "sdr_pipe_fm_lowrate: real-data resampler and filter expected (fm.hs:31-32)");
+    if (r->r.ctx != f->r.ctx) return set_error(SDR_EINVAL, "sdr_pipe_fm_lowrate: records live on different contexts");
+    if (block_size_resampler < f->r.T)
+        return set_error(SDR_EPRECOND, "filter 1: upstream vectors of %d elements are shorter than numCoeffs (%d)", block_size_resampler, f->r.T);
+    sdr_pipe *p;
+    SDR_TRY(new_pipe(r->r.ctx, P_FMLOW, out, &p));
+    p->res = &r->r; p->fir = &f->r; p->in_eb = p->out_eb = 4; p->block_out = block_size_out; p->block_r = block_size_resampler;
+    p->scale_k = scale; p->assert_name = "resample";
+    p->scratch_x.c = p->scratch_y.c = p->ctx;
+    return SDR_OK;
+}
 int sdr_pipe_u8_decimator(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **out) {
     if (!d || block_size_out <= 0) return set_error(SDR_EINVAL, "sdr_pipe_u8_decimator: bad argument");
     if (!d->r.cplx) return set_error(SDR_EINVAL, "sdr_pipe_u8_decimator: the decimator must be a complex-data one (fastDecimatorC)");
@@ -541,7 +659,7 @@ int sdr_pipe_destroy(sdr_pipe_t *p) {
 }
 
 int sdr_pipe_push(sdr_pipe_t *p, const void *in, long long n, int mem) {
-    if (!p || n < 0 || (n && !in) || mem < SDR_HOST || mem > SDR_HOST_PINNED)
+    if (!p || n < 0 || (n && !in) || mem < SDR_HOST || mem > SDR_DEVICE_HELD)
         return set_error(SDR_EINVAL, "sdr_pipe_push: bad argument");
     if (n == 0) return SDR_OK;
     return pipe_push_any(p, in, n, mem);
@@ -593,6 +711,7 @@ int sdr_pipe_sync(sdr_pipe_t *p) {
     if (!p) return set_error(SDR_EINVAL, "sdr_pipe_sync: null handle");
     SDR_TRY(p->ctx->bind());
     SDR_TRY(flush_pending(p));
+    SDR_TRY(materialize_ext(p));   // SDR_DEVICE_HELD vectors are the caller's again after this call
     SDR_CUDA(cudaStreamSynchronize(p->ctx->stream));
     SDR_CUDA(cudaStreamSynchronize(p->ctx->side));
     trace_dump();
@@ -607,9 +726,9 @@ int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs) {
         SDR_TRY(p->ctx->bind());
         SDR_TRY(flush_pending(p));    // a reserve may slide or reallocate: no deferred copy may still target the old place,
         SDR_TRY(fifo_writable(p));    // and no in-flight drain may still be reading it
-        long long in_per_out = (p->kind == P_RESAMP) ? (p->res->M + p->res->L - 1) / p->res->L
+        long long in_per_out = is_resamp_kind(p->kind) ? (p->res->M + p->res->L - 1) / p->res->L
                              : is_byte_fed(p->kind) ? 2 * p->fir->D : p->fir->D;
-        long long taps = (p->kind == P_RESAMP) ? p->res->T : p->fir->T;
+        long long taps = is_resamp_kind(p->kind) ? p->res->T : p->fir->T;
         SDR_TRY(p->in.reserve((size_t)(2 * (min_outputs + p->block_out) * in_per_out + taps) * p->in_eb));
         SDR_TRY(p->fifo.reserve((size_t)(2 * (min_outputs + p->block_out)) * p->out_eb));
     }
@@ -628,7 +747,7 @@ namespace {
 struct StateHeader {
     uint32_t magic, version;
     int32_t  kind, in_eb, out_eb, taps, factor, interp, last_sel, reserved;
-    int64_t  block_out, k_next, pos, n_total, skip, in_bytes, fifo_bytes, n_vecs, last_bytes;
+    int64_t  block_out, k_next, pos, n_total, skip, in_bytes, fifo_bytes, n_vecs, last_bytes, block_r;
 };
 const uint32_t STATE_MAGIC = 0x50524453u;   // "SDRP"
 size_t last_bytes_of(const sdr_pipe *p) {
@@ -640,6 +759,7 @@ void fill_header(const sdr_pipe *p, StateHeader *h) {
     h->magic = STATE_MAGIC; h->version = 1; h->kind = p->kind; h->in_eb = (int32_t)p->in_eb; h->out_eb = (int32_t)p->out_eb;
     if (p->fir) { h->taps = p->fir->T; h->factor = p->fir->D; h->interp = 1; }
     if (p->res) { h->taps = p->res->T; h->factor = p->res->M; h->interp = p->res->L; }
+    if (p->kind == P_FMLOW) { h->reserved = p->fir->T; h->block_r = p->block_r; }
     h->last_sel = p->last_sel; h->block_out = p->block_out; h->k_next = p->k_next; h->pos = p->pos; h->n_total = p->n_total;
     h->skip = p->skip; h->in_bytes = is_fir_kind(p->kind) ? (int64_t)p->in.size() : 0; h->fifo_bytes = (int64_t)p->fifo.size();
     h->n_vecs = (int64_t)p->vec_lens.size(); h->last_bytes = (int64_t)last_bytes_of(p);
@@ -661,6 +781,7 @@ int sdr_pipe_state_save(sdr_pipe_t *p, void *buf, size_t capacity, size_t *writt
     if (!p || !buf) return set_error(SDR_EINVAL, "sdr_pipe_state_save: bad argument");
     SDR_TRY(p->ctx->bind());
     SDR_TRY(flush_pending(p));
+    SDR_TRY(materialize_ext(p));
     SDR_TRY(fifo_writable(p));
     StateHeader h;
     fill_header(p, &h);
@@ -689,7 +810,8 @@ int sdr_pipe_state_restore(sdr_pipe_t *p, const void *buf, size_t bytes) {
     fill_header(p, &mine);
     if (h.magic != STATE_MAGIC || h.version != 1) return set_error(SDR_EINVAL, "sdr_pipe_state_restore: not a pipe state (magic / version)");
     if (h.kind != mine.kind || h.in_eb != mine.in_eb || h.out_eb != mine.out_eb || h.taps != mine.taps || h.factor != mine.factor ||
-        h.interp != mine.interp || h.block_out != mine.block_out || h.last_bytes != mine.last_bytes)
+        h.interp != mine.interp || h.block_out != mine.block_out || h.last_bytes != mine.last_bytes || h.reserved != mine.reserved ||
+        h.block_r != mine.block_r)
         return set_error(SDR_EINVAL, "sdr_pipe_state_restore: the state was saved from a differently constructed stage "
                          "(kind %d/%d, taps %d/%d, factor %d/%d, block %lld/%lld)", h.kind, mine.kind, h.taps, mine.taps, h.factor,
                          mine.factor, (long long)h.block_out, (long long)mine.block_out);
@@ -701,6 +823,7 @@ int sdr_pipe_state_restore(sdr_pipe_t *p, const void *buf, size_t bytes) {
     cudaStream_t st = p->ctx->stream;
     const char *q = (const char *)buf + sizeof(h);
     p->in.rd = p->in.wr = 0; p->fifo.rd = p->fifo.wr = 0; p->vec_lens.clear();
+    p->ext_p = nullptr; p->ext_bytes = 0;
     if (h.in_bytes) {
         SDR_TRY(p->in.reserve((size_t)h.in_bytes));
         SDR_CUDA(cudaMemcpyAsync(p->in.p, q, (size_t)h.in_bytes, cudaMemcpyHostToDevice, st));
@@ -767,7 +890,7 @@ static int drain(sdr_pipe *sink, void *out, long long out_capacity, int out_mem,
 int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_len, long long n_vecs, int in_mem,
                  void *out, long long out_capacity, int out_mem, long long *n_out) {
     if (!p || !sink || vec_len <= 0 || n_vecs < 0 || (n_vecs && !in) || (out_capacity && !out) || !n_out ||
-        in_mem < SDR_HOST || in_mem > SDR_HOST_PINNED || out_mem < SDR_HOST || out_mem > SDR_HOST_PINNED)
+        in_mem < SDR_HOST || in_mem > SDR_DEVICE_HELD || out_mem < SDR_HOST || out_mem > SDR_HOST_PINNED)
         return set_error(SDR_EINVAL, "sdr_pipe_run: bad argument");
     long long written = 0;
     SDR_TRY(p->ctx->bind());
@@ -954,7 +1077,7 @@ int sdr_pipe_connect(sdr_pipe_t *src, sdr_pipe_t *dst) {
     if (src->out_eb != dst->in_eb && !(dst->kind == P_CONVERT))
         return set_error(SDR_EINVAL, "sdr_pipe_connect: element types differ (%zu-byte out, %zu-byte in)", src->out_eb, dst->in_eb);
     if (is_fir_kind(src->kind) && is_fir_kind(dst->kind)) {
-        long long need = (dst->kind == P_RESAMP) ? (dst->res->T + dst->res->L - 1) / dst->res->L : dst->fir->T;
+        long long need = is_resamp_kind(dst->kind) ? (dst->res->T + dst->res->L - 1) / dst->res->L : dst->fir->T;
         if (src->block_out < need)
             return set_error(SDR_EPRECOND, "%s 1: upstream vectors of %lld elements are shorter than numCoeffs (%lld)",
                              dst->assert_name, src->block_out, need);

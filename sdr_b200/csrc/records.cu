@@ -101,6 +101,22 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
         else        SDR_TRY(launch_dec_fast(ctx, cplx, T, D, d_taps, seg, d_out, num, &done, &name));
         if (done > 0) last_kernel = name;
     }
+    if (done == 0 && seg.nb > 0) {
+        // Two segments and nothing for the tuned kernel in the first: a stage's short carried tail in front of vectors it
+        // reads in place.  Only the few windows that START in the tail straddle the boundary -- the generic kernel
+        // computes those (plus at most a few more, up to a 16-byte aligned start in the second segment); everything
+        // after them is a one-segment problem.
+        const long long m_a = (seg.na + D - 1) / D;
+        long long m1 = -1;
+        for (long long m = m_a; m < m_a + 16; m++)
+            if (((((uintptr_t)seg.b) + (size_t)(m * D - seg.na) * eb) & 15) == 0) { m1 = m; break; }
+        if (m1 >= 0 && m1 < num && m1 * D - seg.na < seg.nb) {
+            if (m1 > 0) SDR_TRY(launch_fir_generic(ctx, cplx, T, D, d_taps, seg, d_out, m1));
+            const long long off = m1 * D - seg.na;
+            Seg2 rest = {(const char *)seg.b + (size_t)off * eb, seg.nb - off, nullptr, 0};
+            return run(rest, 0, (char *)d_out + (size_t)m1 * eb, num - m1, cross_order);
+        }
+    }
     if (done < num) {
         Seg2 rest = seg;
         long long skip = done * D;
@@ -210,16 +226,29 @@ int ResRec::run(Seg2 seg, long long first, int g0, void *d_out, long long num, b
     if (ng == L && num >= 4096 && !no_tuned) {
         auto span = [&](long long count) { long long gi = (long long)g0 + count;
                                            return (gi / ng) * sum_inc + prefix[gi % ng] - prefix[g0]; };
+        // first output (on a cycle boundary) whose window starts on a 16-byte boundary; with a short first segment (a
+        // stage's carried tail in front of vectors read in place) the start is looked for in the second one
         long long p0 = -1;
-        for (long long p = 0; p <= 4LL * ng; p++)
-            if ((g0 + p) % ng == 0 && span(p) < seg.na && ((((uintptr_t)seg.a) + (size_t)span(p) * eb) & 15) == 0) { p0 = p; break; }
+        const bool tail_first = seg.nb > 0 && seg.na < 4096;
+        const long long p_limit = 4LL * ng + (tail_first ? (seg.na * L) / M + 2LL * ng : 0);
+        const char *t_ptr = nullptr;
+        long long t_avail = 0;
+        for (long long p = 0; p <= p_limit; p++) {
+            if ((g0 + p) % ng != 0) continue;
+            const long long sp = span(p);
+            const char *ptr;
+            long long avail;
+            if (sp < seg.na) { if (tail_first) continue; ptr = (const char *)seg.a + (size_t)sp * eb; avail = seg.na - sp; }
+            else if (seg.nb > 0 && sp - seg.na < seg.nb) { ptr = (const char *)seg.b + (size_t)(sp - seg.na) * eb; avail = seg.nb - (sp - seg.na); }
+            else break;
+            if ((((uintptr_t)ptr) & 15) == 0) { p0 = p; t_ptr = ptr; t_avail = avail; break; }
+        }
         if (p0 >= 0 && p0 < num) {
             long long done = 0;
             const char *name = nullptr;
             const bool can_fork = ctx->override_st == nullptr;
             if (can_fork) SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
-            SDR_TRY(launch_res_fast(ctx, cplx, L, M, n_taps, d_plain, (const char *)seg.a + (size_t)span(p0) * eb, seg.na - span(p0),
-                                    (char *)d_out + (size_t)p0 * eb, num - p0, &done, &name));
+            SDR_TRY(launch_res_fast(ctx, cplx, L, M, n_taps, d_plain, t_ptr, t_avail, (char *)d_out + (size_t)p0 * eb, num - p0, &done, &name));
             if (done > 0) {
                 last_kernel = name;
                 const bool fork = can_fork;

@@ -223,6 +223,14 @@ class NativePipe:
         v = np.ascontiguousarray(vec, dtype=self.in_dtype)
         L.check(L.lib.sdr_pipe_push(self.h, L.ptr(v), len(v), L.SDR_HOST))
 
+    def push_device(self, dptr, n, held=False):
+        """push a vector that already lives in device memory (n input elements at `dptr`).  held=True (SDR_DEVICE_HELD): the
+        stage reads it in place -- the caller leaves it untouched until sync()"""
+        L.check(L.lib.sdr_pipe_push(self.h, dptr, n, L.SDR_DEVICE_HELD if held else L.SDR_DEVICE))
+
+    def sync(self):
+        L.check(L.lib.sdr_pipe_sync(self.h))
+
     def ready(self):
         n = C.c_int()
         L.check(L.lib.sdr_pipe_ready(self.h, C.byref(n)))

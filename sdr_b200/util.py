@@ -108,6 +108,14 @@ def pipeFmFrontEnd(decimator, blockSizeOut) -> NativePipe:
     return NativePipe(h, decimator.ctx, np.uint8, np.float32, owner=decimator)
 
 
+def pipeFmLowRate(resampler, blockSizeResampler, filt, blockSizeOut, scale) -> NativePipe:
+    """firResampler resampler blockSizeResampler >-> firFilter filt blockSizeOut >-> P.map (VG.map (* scale))  (fm.hs:38-40),
+    fused: float phases in, audio samples out"""
+    h = C.c_void_p()
+    L.check(L.lib.sdr_pipe_fm_lowrate(resampler.handle, blockSizeResampler, filt.handle, blockSizeOut, float(scale), C.byref(h)))
+    return NativePipe(h, resampler.ctx, np.float32, np.float32, owner=(resampler, filt))
+
+
 def pipeU8Decimator(decimator, blockSizeOut) -> NativePipe:
     """P.map interleavedIQUnsignedByteToFloat >-> firDecimator decimator blockSizeOut  (fm.hs:34-36), fused: u8 IQ bytes
     in, complex samples out"""
