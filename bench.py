@@ -943,13 +943,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-batch-vectors", type=int, default=256,
-                    help="sdr_pipe_set_batch: output vectors per launch in the end-to-end run (256 x 8192 outputs = 128 MiB of input)")
+    ap.add_argument("--e2e-batch-vectors", type=int, default=0,
+                    help="sdr_pipe_set_batch: output vectors per launch in the end-to-end run; default 256 / n_gpus (256 x 8192 outputs = "
+                         "128 MiB of input per launch on one GPU; smaller batches on the smaller per-rank streams keep the copy pipeline deep)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.e2e_batch_vectors <= 0:
+        args.e2e_batch_vectors = max(16, 256 // max(1, world))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":

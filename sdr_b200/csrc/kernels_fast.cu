@@ -18,6 +18,8 @@
 //     balanced between HBM and the FP32 pipe (see DESIGN.md roofline).
 #include "ring_common.cuh"
 
+#include <cstdlib>
+
 namespace sdr {
 
 // One instantiation per (data type, stored tap count T, decimation D, outputs per lane R).  T is the kernel's tap
@@ -64,6 +66,9 @@ k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restric
     int cnt = (int)(q + (blockIdx.x < rem ? 1 : 0));   // local sub-tiles 0..cnt-1 are computed; cnt is halo-only
     if (cnt == 0) return;
 
+    // Programmatic dependent launch: let the next kernel in the stream be scheduled as this one's CTAs drain (its launch
+    // latency, CTA start-up and barrier set-up then overlap our tail) ...
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t ring = smem_u32(smem);
     const uint32_t bar_full = ring + C::RING_BYTES + ((128 - C::RING_BYTES % 128) % 128);
     const uint32_t bar_empty = bar_full + C::NS * 8;
@@ -75,6 +80,9 @@ k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restric
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    // ... and, launched that way ourselves, touch global memory only after everything before us in the stream has
+    // completed and flushed (a no-op when the predecessor did not trigger early): stream-order semantics are unchanged
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const unsigned char *gin = reinterpret_cast<const unsigned char *>(in);
     // The stream is `in` (a_bytes bytes) followed by `in_b` (up to total_bytes; the right neighbour's chunk on a sharded
@@ -261,10 +269,29 @@ static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long 
     if (sms < 1) sms = 1;
     int grid = (int)(n_sub < sms ? n_sub : sms);
     const long long num_mask = covering ? num : n_sub * C::SUB_OUT;
-    k_dec_ring<CPLX, T, D, R><<<grid, 256, C::SMEM_BYTES, c->s()>>>(seg.a, a_bytes, seg.b, total_bytes, d_out, num_mask, d_taps, n_sub);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = c->s();
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        static const bool no_pdl = getenv("SDR_B200_NO_PDL") != nullptr;   // measurement knob
+        cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+        const void *a0 = seg.a, *b0 = seg.b;
+        SDR_CUDA(cudaLaunchKernelEx(&cfg, k_dec_ring<CPLX, T, D, R>, a0, a_bytes, b0, total_bytes, d_out, num_mask, d_taps, n_sub));
+    }
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     return SDR_OK;
+}
+
+// true when launch_dec_fast would produce ALL `num` outputs in one launch (no generic tail to fork): same conditions as
+// the covering mode of launch_ring
+bool dec_fast_will_cover(bool cplx, int taps_stored, int D, Seg2 seg, long long num) {
+    if (num <= 0 || taps_stored > 128 || (D != 4 && D != 8 && D != 16)) return false;
+    const int epc = cplx ? 2 : 4;
+    return (((uintptr_t)seg.a) & 15) == 0 && (seg.na % epc) == 0 && (seg.nb == 0 || (((uintptr_t)seg.b) & 15) == 0) &&
+           ((seg.na + seg.nb) % epc) == 0;
 }
 
 // x = seg.a ++ seg.b.  taps_stored = the record's tap count (d_taps is zero-padded to at least 128 floats).

@@ -91,11 +91,15 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
     last_kernel = "fir_direct";
     static const bool no_fork = getenv("SDR_B200_NOFORK") != nullptr;   // debugging aid: keep the tail on the main stream
     const bool can_fork = ctx->override_st == nullptr && !no_fork;
+    bool fork_recorded = false;
     {
         // tuned kernel over the part of the FIRST segment it can take; the rest (ragged tail, straddling windows)
         // is finished by the generic kernel in the same tap order.  The tail only depends on the INPUT, so it runs
         // on the side stream concurrently with the tuned kernel (fork before, join after).
-        if (can_fork) SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        // (no event when the tuned kernel will take everything: an event between two passes would also keep the next
+        // pass from being scheduled early, see the programmatic dependent launch in kernels_fast.cu)
+        const bool covers = D > 2 && dec_fast_will_cover(cplx, T, D, seg, num);
+        if (can_fork && !covers) { SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); fork_recorded = true; }
         const char *name = nullptr;
         if (D <= 2) SDR_TRY(launch_fir_small_stride_fast(ctx, cplx, T, D, d_taps, seg.a, seg.na, d_out, num, &done, &name));
         else        SDR_TRY(launch_dec_fast(ctx, cplx, T, D, d_taps, seg, d_out, num, &done, &name));
@@ -123,7 +127,7 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
         if (skip >= rest.na) { rest.a = (const char *)rest.b + (skip - rest.na) * eb; rest.na = rest.nb - (skip - rest.na);
                                rest.b = nullptr; rest.nb = 0; if (rest.na < 0) rest.na = 0; }
         else                 { rest.a = (const char *)rest.a + skip * eb; rest.na -= skip; }
-        const bool fork = can_fork && done > 0;
+        const bool fork = can_fork && done > 0 && fork_recorded;
         if (fork) { SDR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0)); ctx->override_st = ctx->side; }
         int rc = launch_fir_generic(ctx, cplx, T, D, d_taps, rest, (char *)d_out + done * eb, num - done);
         if (fork) {
