@@ -889,6 +889,33 @@ def run_pipes_mode(args, ctx, dec, sdr_b200, L):
             res[f"batch_{batch}{tag}"] = {"value": n / (ms * 1e-3) / 1e6, "ms": ms, "launches_per_pass": (ctx.launches - l0) / 3,
                                           "input_vectors_per_launch": (n // BUF) / max(1.0, (ctx.launches - l0) / 3)}
             pipe.close()
+    # the persistent consumer: no launches at all, a push is one store the resident kernel polls.  A longer stream (2^28
+    # samples = 32768 vectors) so that opening / closing the session (~0.1 ms) is amortised as it is in a running receiver.
+    x.free(); y.free()
+    n2 = 1 << min(args.log2n, 28)
+    x = ctx.alloc(8 * n2 + 256)
+    y = ctx.alloc(n2 + 8 * BUF + 256)
+    ctx.synth_noise(x, 2 * n2)
+    pipe = sdr_b200.pipeFirDecimator(dec, BUF)
+    L.check(L.lib.sdr_pipe_set_persistent(pipe.h, n2))
+
+    def run_p():
+        L.check(L.lib.sdr_pipe_run(pipe.h, pipe.h, x.ptr, BUF, n2 // BUF, L.SDR_DEVICE_HELD, y.ptr, n2 // FACTOR + BUF, L.SDR_DEVICE, C.byref(n_out)))
+    for _ in range(2):
+        run_p()
+    ctx.sync()
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    for _ in range(3):
+        run_p()
+    ctx.sync()
+    ms = (time.perf_counter() - t0) * 1e3 / 3
+    res["persistent"] = {"value": n2 / (ms * 1e-3) / 1e6, "ms": ms, "samples": n2, "vectors_per_pass": n2 // BUF,
+                         "launches_per_pass": (ctx.launches - l0) / 3, "kernel": "dec_c_ring_persist<128,8,8,32>",
+                         "note": "wall clock per pass of 8192-sample SDR_DEVICE_HELD pushes, one vector per push (sdr_pipe_set_persistent): ONE "
+                                 "resident kernel per pass consumes them as they are published; includes opening and closing the session, "
+                                 "the ordinary launch for what it leaves and the device-to-device copies of the yielded vectors"}
+    pipe.close()
     res["note"] = ("batch_N: launch threshold of N output vectors (N = 0: as soon as one 8192-sample output vector completes = every 8 input "
                    "vectors); default rows push SDR_DEVICE_HELD vectors (read in place, zero-copy), *_copied rows push SDR_DEVICE vectors "
                    "(one device-to-device copy per vector into the stage, round 1's only mode)")

@@ -317,6 +317,14 @@ int sdr_pipe_sync(sdr_pipe_t *p);
 /* throughput knob for FIR stages: do not launch before `min_outputs` new outputs are computable (default 0 = as soon
  * as one output vector can be completed, the lowest latency).  Yielded vectors are unchanged, only their timing. */
 int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs);
+/* Per-vector device pushes without a launch per vector (the Pipes per-8192 contract of firDecimator, Filter.hs:578-598, on
+ * the device): with max_session_samples > 0, SDR_DEVICE_HELD vectors pushed back to back (adjacent in memory) are consumed by
+ * a RESIDENT kernel -- a push is one store into a page-locked control block the kernel polls, sdr_pipe_ready / _pop see the
+ * runs it has published as finished.  A session ends at sdr_pipe_sync, at a vector that is not adjacent, or after
+ * max_session_samples (the output FIFO is sized for that up front); the ordinary launch path finishes what a session leaves
+ * (the carried tail, an incomplete run).  The kernel leaves 8 SMs free; a warp that waits > 3 s for input abandons the session
+ * with an error instead of hanging the GPU.  Complex decimate-by-8 stages with 65..128 stored taps only; 0 switches it off. */
+int sdr_pipe_set_persistent(sdr_pipe_t *p, long long max_session_samples);
 /* `runEffect $ each vectors >-> p >-> ... >-> sink >-> collect` as one native loop: pushes n_vecs consecutive vectors of
  * vec_len input elements starting at `in` into `p`, pops every vector `sink` yields (sink = p, or the last stage
  * connected behind it) into `out` back to back, then sdr_pipe_sync.  *n_out = elements written (<= out_capacity). */

@@ -168,6 +168,7 @@ _sig("sdr_pipe_state_save", _P, _P, _SZ, C.POINTER(_SZ))
 _sig("sdr_pipe_state_restore", _P, _P, _SZ)
 _sig("sdr_pipe_sync", _P)
 _sig("sdr_pipe_set_batch", _P, _LL)
+_sig("sdr_pipe_set_persistent", _P, _LL)
 _sig("sdr_pipe_next_len", _P, C.POINTER(_LL))
 _sig("sdr_pipe_run", _P, _P, _P, _LL, _LL, _I, _P, _LL, _I, C.POINTER(_LL))
 _sig("sdr_pipe_run_fd", _P, _P, _I, _LL, _LL, _I, _I, C.POINTER(IoStats))

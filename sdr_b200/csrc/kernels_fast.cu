@@ -326,4 +326,261 @@ int launch_dec_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_ta
     return SDR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent consumer: the ring decimator fed by a flag-published stream (the Pipes per-vector contract on the device
+// without a launch per vector).  The host publishes how many bytes of a contiguous device-resident stream are valid in a
+// page-locked control block the kernel polls; the kernel publishes the runs it has finished in the same block.
+//
+//   * work unit = a RUN of PB consecutive sub-tiles (PB * 32 * R outputs); run r belongs to CTA r % G.  A CTA's tiles
+//     form one sequence t = q * (PB + 1) + j over its runs q: j < PB is a computed sub-tile, j == PB is the halo-only
+//     slot behind the run (the head of the next run, which another CTA computes).  The shared-memory ring, the TMA fills
+//     and the mbarrier protocol are those of k_dec_ring and keep flowing across runs: there is no per-run bubble while the
+//     input is ahead.
+//   * a fill is issued only once its whole run (halo included) has been published.  The warp that frees a slot refills it
+//     if the target run is already available (no waiting); otherwise the warp that will CONSUME the tile issues the fill
+//     itself once the run arrives -- a per-slot claim word (shared-memory CAS on the generation) makes exactly one of them
+//     do it.  So a warp only ever waits for input it needs itself, and every published run is computed even if nothing
+//     further is ever published.
+//   * when the last sub-tile of a run has been stored (per-run counter in shared memory), the run's flag is set in host
+//     memory behind a system-scope fence; the host then pops its outputs with ordinary copies on another stream.
+//   * `closed` ends the session: runs not completely published by then are left to the ordinary launch path.  A warp that
+//     waits for input longer than ~3 s sets `error` and leaves (the host never gets a stuck GPU).
+struct PersistCtl {                      // lives in cudaHostAllocMapped memory; one cache line per writer
+    volatile long long published_bytes;  // host -> device
+    volatile int closed;                 // host -> device
+    int pad0_[13];
+    volatile int error;                  // device -> host (byte 64)
+    int pad1_[15];
+    volatile unsigned int done[1];       // device -> host (byte 128): done[r] = 1 when run r is complete
+};
+// what the relay CTA copies from host memory into device memory for the worker CTAs to poll: 1100 warps polling a host
+// cache line over PCIe would both saturate the link with reads and slow the host's stores to that line to a crawl
+struct PersistRelay { volatile long long avail; volatile int closed; volatile int error; };
+
+template <bool CPLX, int T, int D, int R, int PB>
+__global__ void __launch_bounds__(256, 1)
+k_dec_ring_persist(const void *__restrict__ in, void *__restrict__ out, const float *__restrict__ taps, PersistCtl *ctl,
+                   PersistRelay *relay, long long runs_total) {
+    typedef RingCfg<CPLX, T, D, R> C;
+    static_assert(CPLX, "the persistent consumer is instantiated for complex data");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x - 1, cta = blockIdx.x;
+    if (cta == G) {
+        // the relay CTA (one thread): host memory -> device memory, until the session is closed.  `closed` is read before
+        // the byte count and written after it, so a count seen together with closed == 1 is final.
+        if (threadIdx.x != 0) return;
+        unsigned long long t_last, t_now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_last));
+        long long prev = -1;
+        for (;;) {
+            const int c = ctl->closed;
+            __threadfence_system();                      // the byte count is read AFTER the flag
+            const long long a = ctl->published_bytes;
+            relay->avail = a;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(&relay->closed), "r"(c) : "memory");
+            if (c || relay->error) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+            if (a != prev) { prev = a; t_last = t_now; }
+            else if (t_now - t_last > 3000000000ULL) { relay->error = 1; ctl->error = 1; relay->closed = 1; break; }   // idle for 3 s
+        }
+        return;
+    }
+    const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    constexpr long long SUB_BYTES = 32LL * C::SEG_BYTES;
+    constexpr int PERIOD = PB + 1;
+
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t bar_full = ring + C::RING_BYTES + ((128 - C::RING_BYTES % 128) % 128);
+    const uint32_t bar_empty = bar_full + C::NS * 8;
+    const uint32_t gen_armed = bar_empty + C::NS * 8;
+    __shared__ int s_claim[C::NS];       // last generation of each slot whose fill has been claimed
+    __shared__ int s_run_cnt[8];         // sub-tiles stored per run in flight (indexed by q % 8)
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::NS; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 2);
+                                          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(gen_armed + 4 * s), "r"(0) : "memory");
+                                          s_claim[s] = 0; }
+        for (int i = 0; i < 8; i++) s_run_cnt[i] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned char *gin = reinterpret_cast<const unsigned char *>(in);
+    long long avail = 0;      // bytes known to be published (warp-uniform cache of ctl->published_bytes)
+    int closed = 0;
+    auto run_of = [&](int t) -> long long { return (long long)(t / PERIOD) * G + cta; };
+    auto need_of_run = [&](long long r) -> long long { return ((r + 1) * PB * 32 + C::HALO_SEGS) * (long long)C::SEG_BYTES; };
+    // refresh the cache from host memory (one lane reads, all lanes get the values); `closed` is read FIRST so that a
+    // byte count read after it is final
+    auto refresh = [&]() {
+        long long a = 0; int c = 0;
+        if (lane == 0) {   // device memory (L2), written by the relay CTA; the acquire orders the count's load after the flag's
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(c) : "l"(&relay->closed) : "memory");
+            a = relay->avail;
+        }
+        closed = __shfl_sync(0xffffffffu, c, 0);
+        avail = __shfl_sync(0xffffffffu, a, 0);
+    };
+    auto have_run = [&](long long r, bool wait) -> bool {
+        const long long need = need_of_run(r);
+        if (avail >= need) return true;
+        if (closed) return false;
+        refresh();
+        if (avail >= need || !wait) return avail >= need;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (avail < need) {
+            if (closed) return false;
+            __nanosleep(400);
+            refresh();
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ULL) { if (lane == 0) { relay->error = 1; ctl->error = 1; } closed = 1; return false; }
+            if (relay->error) { closed = 1; return false; }
+        }
+        return true;
+    };
+    // fill tile t (all lanes): its run is known to be published
+    auto issue_fill = [&](int t) {
+        const int slot = t % C::NS, j = t % PERIOD;
+        const int nseg = (j == PB) ? C::HALO_SEGS : 32;
+        const long long g = ((long long)(t / PERIOD) * G + cta) * PB + j;    // global sub-tile (j == PB: head of the next run)
+        uint32_t bytes = nseg * C::SEG_BYTES + (slot == 0 ? C::HALO_SEGS * C::SEG_BYTES : 0);
+        uint32_t bar = bar_full + 8 * slot;
+        if (lane == 0) mbar_expect_tx(bar, bytes);
+        __syncwarp();
+        const unsigned char *src = gin + g * SUB_BYTES + lane * C::SEG_BYTES;
+        if (lane < nseg) bulk_g2s(ring + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE, src, C::SEG_BYTES, bar);
+        if (slot == 0 && lane < C::HALO_SEGS)
+            bulk_g2s(ring + C::NS * C::SLOT_BYTES + lane * C::SEG_STRIDE, src, C::SEG_BYTES, bar);
+        if (lane == 0) gen_publish(gen_armed + 4 * slot, t / C::NS + 1);
+    };
+    // make sure tile t's fill has been issued by exactly one warp: whoever moves the slot's claim word from gen-1 to gen
+    auto claim_and_fill = [&](int t) {
+        const int slot = t % C::NS, gen = t / C::NS + 1;
+        int won = 0;
+        // (a plain look first: in the steady state the fill was claimed long ago by the warp that freed the slot)
+        if (lane == 0 && *(volatile int *)&s_claim[slot] == gen - 1) won = atomicCAS(&s_claim[slot], gen - 1, gen) == gen - 1;
+        won = __shfl_sync(0xffffffffu, won, 0);
+        if (!won) return;
+        if (gen > 1) mbar_wait(bar_empty + 8 * slot, (gen - 2) & 1);   // the previous generation has been consumed
+        issue_fill(t);
+    };
+
+    float tap[T];
+#pragma unroll
+    for (int k = 0; k < T; k++) tap[k] = __ldg(taps + k);
+
+    // prologue: fill the ring with whatever is already published (never waits)
+    for (int t = warp; t < C::NS; t += C::NWARPS)
+        if (run_of(t) < runs_total && have_run(run_of(t), false)) claim_and_fill(t);
+
+    // Run bookkeeping is deferred by one tile: the fence that orders a tile's output stores before the run counter is
+    // cheap once the stores have drained (a tile later) and expensive right behind them.  Before a warp waits for input
+    // it publishes what it holds, so a stalled stream still sees every finished run.
+    int pend_q = -1;
+    long long pend_r = 0;
+    auto publish_pending = [&]() {
+        if (pend_q < 0) return;
+        if (lane == 0) {
+            // CTA scope is enough here: the warps of a run synchronise through the shared-memory counter, and the one that
+            // completes the run issues the (cumulative) system-scope fence before the flag
+            __threadfence_block();
+            if (atomicAdd(&s_run_cnt[pend_q & 7], 1) == PB - 1) {
+                s_run_cnt[pend_q & 7] = 0;
+                __threadfence_system();
+                ctl->done[pend_r] = 1u;
+            }
+        }
+        pend_q = -1;
+    };
+
+    for (int t = warp; ; t += C::NWARPS) {
+        const int q = t / PERIOD, j = t % PERIOD;
+        const long long r = run_of(t);
+        if (r >= runs_total) break;                                   // out of the session's capacity
+        if (!have_run(r, false)) {
+            publish_pending();
+            if (!have_run(r, true)) break;                            // closed: this run will never exist
+        }
+        claim_and_fill(t);                                             // unless the warp that freed the slot already did
+        const int slot = t % C::NS, slot2 = (t + 1) % C::NS;
+        if (j == PB) {
+            // halo-only slot: nothing to compute; the consumer of t-1 arrives for having read it, this warp for "owning" it.
+            // The arrival must count for THIS generation: wait until its fill has landed first (another warp may have claimed
+            // the fill and still be waiting for the previous generation's readers -- an early arrival would complete their
+            // phase for them and let the slot be overwritten under a reader).
+            slot_wait<true>(bar_full + 8 * slot, gen_armed + 4 * slot, t / C::NS + 1);
+            if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+        } else {
+            slot_wait<true>(bar_full + 8 * slot, gen_armed + 4 * slot, t / C::NS + 1);
+            slot_wait<true>(bar_full + 8 * slot2, gen_armed + 4 * slot2, (t + 1) / C::NS + 1);
+            const unsigned char *base = smem + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE;
+            u64 acc[R];
+#pragma unroll
+            for (int rr = 0; rr < R; rr++) acc[rr] = 0ULL;
+#pragma unroll
+            for (int c = 0; c < C::NCH; c++) {
+                const int e0 = c * 2;
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(base + (e0 / C::SEG_ELEMS) * C::SEG_STRIDE + (e0 % C::SEG_ELEMS) * 8);
+#pragma unroll
+                for (int rr = 0; rr < R; rr++) {
+                    const int k0 = e0 - rr * D, k1 = e0 + 1 - rr * D;
+                    if (k0 >= 0 && k0 < T) acc[rr] = ffma2(v.x, dup2(tap[k0 < 0 ? 0 : (k0 >= T ? 0 : k0)]), acc[rr]);
+                    if (k1 >= 0 && k1 < T) acc[rr] = ffma2(v.y, dup2(tap[k1 < 0 ? 0 : (k1 >= T ? 0 : k1)]), acc[rr]);
+                }
+            }
+            const long long m0 = (r * PB + j) * (long long)C::SUB_OUT + lane * R;
+            u64 *os = reinterpret_cast<u64 *>(out) + m0;
+            if (vec_store) {
+                ulonglong2 *o = reinterpret_cast<ulonglong2 *>(os);
+#pragma unroll
+                for (int rr = 0; rr < R; rr += 2) o[rr / 2] = make_ulonglong2(acc[rr], acc[rr + 1]);
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < R; rr++) os[rr] = acc[rr];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_empty + 8 * slot);
+                if (j == 0) mbar_arrive(bar_empty + 8 * slot);   // the first sub-tile of a run has no predecessor using it as halo
+                mbar_arrive(bar_empty + 8 * slot2);
+            }
+            publish_pending();          // the PREVIOUS tile of this warp
+            pend_q = q; pend_r = r;
+        }
+        // opportunistic refill of the slot just freed -- only if the target's run is already published (never waits for input)
+        const int t2 = t + C::NS;
+        const long long r2 = run_of(t2);
+        if (r2 < runs_total && have_run(r2, false)) claim_and_fill(t2);
+    }
+    publish_pending();
+}
+
+// launches the persistent consumer on `stream` over the contiguous device stream at d_in; grid = SMs - reserve
+int launch_dec_persist(Ctx *c, int taps_stored, int D, bool cplx, const float *d_taps, const void *d_in, void *d_out, void *ctl,
+                       void *d_relay, long long runs_total, cudaStream_t stream, int *run_samples, int *halo_samples, int *grid_out,
+                       const char **name) {
+    *name = "none";
+    if (!cplx || D != 8 || taps_stored > 128 || taps_stored <= 64) return set_error(SDR_EINVAL, "no persistent kernel for this shape");
+    typedef RingCfg<true, 128, 8, 8> C;
+    constexpr int PB = 32;          // a run = 32 sub-tiles = 8192 outputs = one yielded vector of the headline configuration
+    SDR_TRY(c->bind());
+    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_ring_persist<true, 128, 8, 8, PB>), C::SMEM_BYTES));
+    int grid = c->sm_count - 8;     // worker CTAs; one more CTA relays the control block; the remaining SMs stay free for
+                                    // whatever else the process launches while the consumer is resident
+    if (grid < 1) grid = 1;
+    *run_samples = PB * C::SUB_OUT * 8;
+    *halo_samples = C::HALO_SEGS * C::SEG_ELEMS;
+    *grid_out = grid;
+    *name = "dec_c_ring_persist<128,8,8,32>";
+    SDR_CUDA(cudaMemsetAsync(d_relay, 0, sizeof(PersistRelay), stream));
+    k_dec_ring_persist<true, 128, 8, 8, PB><<<grid + 1, 256, C::SMEM_BYTES, stream>>>(d_in, d_out, d_taps, (PersistCtl *)ctl,
+                                                                                       (PersistRelay *)d_relay, runs_total);
+    c->launches++;
+    SDR_CUDA(cudaGetLastError());
+    return SDR_OK;
+}
+
 }  // namespace sdr

@@ -29,9 +29,11 @@ struct LinBuf {
     Ctx *c = nullptr;
     char *p = nullptr;
     size_t cap = 0, rd = 0, wr = 0;
+    bool fixed = false;   // a persistent consumer writes into this buffer: it must neither move nor rewind
     size_t size() const { return wr - rd; }
     int reserve(size_t more) {   // make room for `more` bytes after wr, keeping [rd, wr)
         if (wr + more <= cap) return SDR_OK;
+        if (fixed) return set_error(SDR_ENOMEM, "buffer is held in place by a persistent consumer session (%zu more bytes wanted)", more);
         size_t live = size();
         if (live + more <= cap && rd >= live) {   // slide the live region to the front (regions do not overlap)
             if (live) SDR_CUDA(cudaMemcpyAsync(p, p + rd, live, cudaMemcpyDeviceToDevice, c->stream));
@@ -47,7 +49,7 @@ struct LinBuf {
         p = np; cap = ncap; rd = 0; wr = live;
         return SDR_OK;
     }
-    void consume(size_t bytes) { rd += bytes; if (rd == wr) rd = wr = 0; }
+    void consume(size_t bytes) { rd += bytes; if (rd == wr && !fixed) rd = wr = 0; }
     // move the (small) live region so that it starts `lead` bytes past a 16-byte boundary at the front of the buffer;
     // skipped when source and destination would overlap
     int realign(size_t lead) {
@@ -107,6 +109,22 @@ enum { MEM_FWD = 100 };   // internal: a connected upstream stage hands over its
 
 using namespace sdr;
 
+// A persistent-consumer session (kernels_fast.cu: k_dec_ring_persist): the resident kernel, its page-locked control block
+// and where its input run and its outputs live.
+struct PersistSession {
+    bool open = false;
+    void *ctl = nullptr; size_t ctl_bytes = 0;   // cudaHostAllocMapped: header + one done flag per run
+    void *d_relay = nullptr;                     // device copy of (published, closed) kept current by the kernel's relay CTA
+    cudaStream_t stream = nullptr;               // the consumer's own stream (the ctx stream stays free for everything else)
+    cudaEvent_t ev = nullptr;
+    const char *base = nullptr;                  // first byte of the session's in-place input run
+    long long runs_total = 0, runs_popped = 0;   // capacity / runs whose outputs have been handed to the FIFO
+    int run_samples = 0, halo_samples = 0, grid = 0;
+    size_t fifo_base = 0;                        // FIFO offset of run 0's outputs
+    long long capacity_bytes = 0;
+    const char *kernel = "none";
+};
+
 struct sdr_pipe {
     int kind = 0;
     Ctx *ctx = nullptr;
@@ -147,6 +165,8 @@ struct sdr_pipe {
     const char *ext_p = nullptr;
     size_t ext_bytes = 0;
     long long block_r = 0;            // fused low-rate stage: the resampler stage's own vector length (its yields gate the filter)
+    long long persist_max = 0;        // > 0: in-place runs are consumed by a persistent kernel, sessions of at most this many samples
+    PersistSession ps;
 };
 
 namespace sdr {
@@ -200,6 +220,115 @@ static void consume_input(sdr_pipe *p, size_t bytes) {
     const size_t rest = bytes - live;
     p->ext_p += rest; p->ext_bytes -= rest;
     if (p->ext_bytes == 0) p->ext_p = nullptr;
+}
+
+// ---- persistent consumer sessions ---------------------------------------------------------------------------------------
+// layout of kernels_fast.cu's PersistCtl: one cache line per writer (host: bytes 0..63, device: 64.., flags from 128)
+struct PersistHdr { volatile long long published_bytes; volatile int closed; int pad0_[13]; volatile int error; int pad1_[15]; };
+static_assert(sizeof(PersistHdr) == 128, "control block layout");
+static volatile unsigned int *persist_flags(PersistSession &S) { return (volatile unsigned int *)((char *)S.ctl + sizeof(PersistHdr)); }
+
+// hand the outputs of every run that has completed (in order) to the FIFO
+static void persist_poll(sdr_pipe *p) {
+    PersistSession &S = p->ps;
+    if (!S.open) return;
+    volatile unsigned int *done = persist_flags(S);
+    long long r = S.runs_popped;
+    while (r < S.runs_total && done[r]) r++;
+    if (r != S.runs_popped) {
+        S.runs_popped = r;
+        p->fifo.wr = S.fifo_base + (size_t)r * (size_t)(S.run_samples / p->fir->D) * p->out_eb;
+    }
+}
+
+// end the session: the kernel finishes every completely published run and exits; what is left of the in-place run (the
+// carried tail and an incomplete run) goes back to the ordinary launch path
+static int persist_close(sdr_pipe *p) {
+    PersistSession &S = p->ps;
+    if (!S.open) return SDR_OK;
+    PersistHdr *h = (PersistHdr *)S.ctl;
+    static const bool dbg = getenv("SDR_B200_PERSIST_DEBUG") != nullptr;
+    if (dbg) { persist_poll(p); fprintf(stderr, "[persist] closing: published %lld bytes, %lld of %lld runs popped so far\n", (long long)h->published_bytes, S.runs_popped, S.runs_total); }
+    __sync_synchronize();
+    h->closed = 1;
+    __sync_synchronize();
+    SDR_CUDA(cudaStreamSynchronize(S.stream));
+    persist_poll(p);
+    S.open = false;
+    p->fifo.fixed = false;
+    const long long pub_samples = h->published_bytes / (long long)p->in_eb;
+    const long long runs_final = pub_samples >= S.halo_samples ? (pub_samples - S.halo_samples) / S.run_samples : 0;
+    // h->error: a warp waited more than 3 s for input and the kernel wound itself down (an idle stream must not keep a
+    // spinning kernel resident for ever).  Not a failure: the runs it did finish count, the rest is computed again.
+    if (!h->error && S.runs_popped != (runs_final < S.runs_total ? runs_final : S.runs_total))
+        return set_error(SDR_ECUDA, "persistent consumer: %lld runs completed, %lld expected", S.runs_popped, runs_final);
+    consume_input(p, (size_t)S.runs_popped * (size_t)S.run_samples * p->in_eb);
+    return SDR_OK;
+}
+
+// open a session on the in-place run if there is none, publish what has arrived; false: the ordinary path must take over
+static int persist_try(sdr_pipe *p, bool *taken) {
+    *taken = false;
+    PersistSession &S = p->ps;
+    FirRec &f = *p->fir;
+    if (!S.open) {
+        if (!p->ext_bytes || p->skip != 0) return SDR_OK;
+        SDR_TRY(flush_pending(p));
+        SDR_TRY(fifo_writable(p));
+        if (p->in.size() != 0) {
+            // bridge: the windows that START in the carried tail straddle the stage's own buffer and the in-place run; one
+            // small ordinary launch computes them, after which the stream continues inside the run alone
+            const long long na = (long long)(p->in.size() / p->in_eb), nb = (long long)(p->ext_bytes / p->in_eb);
+            const long long m1 = (na + f.D - 1) / f.D;
+            if (m1 * f.D - na + f.T > nb) return SDR_OK;                      // not enough of the run yet
+            SDR_TRY(p->fifo.reserve((size_t)m1 * p->out_eb));
+            SDR_TRY(launch_fir_generic(p->ctx, f.cplx, f.T, f.D, f.d_taps, input_seg(p), p->fifo.p + p->fifo.wr, m1));
+            p->fifo.wr += (size_t)m1 * p->out_eb;
+            consume_input(p, (size_t)(m1 * f.D) * p->in_eb);
+        }
+        if ((((uintptr_t)p->ext_p) & 15) != 0) return SDR_OK;
+        if (!S.stream) {
+            SDR_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+            SDR_CUDA(cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming));
+        }
+        // geometry of the kernel that will serve the shape (also validates the shape)
+        S.run_samples = 32 * 256 * f.D; S.halo_samples = 128;   // checked against the launcher below
+        const long long max_samples = p->persist_max;
+        const long long out_bytes = (max_samples / f.D + 1) * (long long)p->out_eb;
+        SDR_TRY(p->fifo.reserve((size_t)out_bytes));
+        const long long runs_total = max_samples / S.run_samples;
+        const size_t need = sizeof(PersistHdr) + (size_t)(runs_total + 1) * 4;
+        if (need > S.ctl_bytes) {
+            if (S.ctl) SDR_CUDA(cudaFreeHost(S.ctl));
+            S.ctl = nullptr; S.ctl_bytes = 0;
+            SDR_CUDA(cudaHostAlloc(&S.ctl, need, cudaHostAllocMapped));
+            S.ctl_bytes = need;
+        }
+        memset(S.ctl, 0, need);
+        S.runs_total = runs_total; S.runs_popped = 0;
+        if (!S.d_relay) SDR_CUDA(cudaMalloc(&S.d_relay, 64));
+        S.base = p->ext_p; S.fifo_base = p->fifo.wr;
+        S.capacity_bytes = runs_total * (long long)S.run_samples * (long long)p->in_eb + (long long)S.halo_samples * (long long)p->in_eb;
+        __sync_synchronize();
+        void *d_ctl = nullptr;
+        SDR_CUDA(cudaHostGetDevicePointer(&d_ctl, S.ctl, 0));
+        // everything enqueued on the ctx stream so far (what produced the FIFO's contents, tail copies) precedes the consumer
+        SDR_CUDA(cudaEventRecord(S.ev, p->ctx->stream));
+        SDR_CUDA(cudaStreamWaitEvent(S.stream, S.ev, 0));
+        int rs = 0, hs = 0;
+        SDR_TRY(launch_dec_persist(p->ctx, f.T, f.D, f.cplx, f.d_taps, S.base, p->fifo.p + S.fifo_base, d_ctl, S.d_relay, runs_total, S.stream,
+                                   &rs, &hs, &S.grid, &S.kernel));
+        if (rs != S.run_samples || hs != S.halo_samples) return set_error(SDR_EINVAL, "persistent consumer: geometry mismatch");
+        p->fifo.fixed = true;
+        S.open = true;
+        f.last_kernel = S.kernel;
+    }
+    if (p->ext_p != S.base || (long long)p->ext_bytes > S.capacity_bytes) { SDR_TRY(persist_close(p)); return SDR_OK; }
+    PersistHdr *h = (PersistHdr *)S.ctl;
+    __sync_synchronize();                    // the vectors were complete before they were pushed (SDR_DEVICE_HELD contract)
+    h->published_bytes = (long long)p->ext_bytes;
+    *taken = true;
+    return SDR_OK;
 }
 
 static int pipe_push_dev(sdr_pipe *p, const void *d_src, long long n);
@@ -391,7 +520,7 @@ static int process_fm_low(sdr_pipe *p, long long fifo_have, long long batch) {
 // run whatever the stream now allows (FIR kinds); data already appended to p->in
 static int process_fir(sdr_pipe *p, bool force = false) {
     long long have = in_elems(p);
-    const long long fifo_have = (long long)(p->fifo.size() / p->out_eb);
+    long long fifo_have = (long long)(p->fifo.size() / p->out_eb);
     const long long batch = (force || p->batch_min < p->block_out) ? p->block_out : p->batch_min;
     if (p->kind == P_RESAMP) {
         ResRec &r = *p->res;
@@ -427,6 +556,16 @@ static int process_fir(sdr_pipe *p, bool force = false) {
     if (p->kind == P_U8DECIM) return process_u8_decim(p, fifo_have, batch);
     if (p->kind == P_FMLOW) return process_fm_low(p, fifo_have, batch);
     FirRec &f = *p->fir;
+    if (p->persist_max > 0) {
+        if (!force) {
+            bool taken = false;
+            SDR_TRY(persist_try(p, &taken));
+            if (taken) return SDR_OK;            // the resident kernel consumes the in-place run as it is published
+        }
+        SDR_TRY(persist_close(p));               // flush, or the run no longer qualifies: finish with ordinary launches
+        have = in_elems(p);
+        fifo_have = (long long)(p->fifo.size() / p->out_eb);
+    }
     long long count = (have >= f.T) ? (have - f.T) / f.D + 1 : 0;
     if (count > 0 && fifo_have + count >= p->block_out && (fifo_have + count >= batch)) {
         SDR_TRY(flush_pending(p));
@@ -477,6 +616,20 @@ static int fetch(sdr_pipe *p, void *d_dst, const void *src, size_t bytes, int me
 static thread_local bool g_bound = false;   // sdr_pipe_run binds the device once for its whole loop
 
 static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, long long n_vecs) {
+    if (p->ps.open) {
+        // fast path of an open persistent session: one more adjacent vector = one store the resident kernel will see
+        const size_t bytes = (size_t)n * p->in_eb;
+        if (mem == SDR_DEVICE_HELD && p->ext_p + p->ext_bytes == (const char *)src && n >= p->fir->T &&
+            (long long)(p->ext_bytes + bytes) <= p->ps.capacity_bytes && !((PersistHdr *)p->ps.ctl)->error) {
+            p->ext_bytes += bytes;
+            p->n_total += n;
+            ((PersistHdr *)p->ps.ctl)->published_bytes = (long long)p->ext_bytes;
+            if (p->downstream) { persist_poll(p); return forward(p); }
+            return SDR_OK;
+        }
+        if (!g_bound) SDR_TRY(p->ctx->bind());
+        SDR_TRY(persist_close(p));
+    }
     if (!g_bound) SDR_TRY(p->ctx->bind());
     TraceScope tr_push(trace_mode() == 1 ? "push(total)" : nullptr, p->ctx, n);
     if (is_fir_kind(p->kind)) {
@@ -647,6 +800,11 @@ int sdr_pipe_destroy(sdr_pipe_t *p) {
     p->ctx->bind();
     cudaStreamSynchronize(p->ctx->stream);
     cudaStreamSynchronize(p->ctx->side);
+    persist_close(p);
+    if (p->ps.stream) cudaStreamDestroy(p->ps.stream);
+    if (p->ps.ev) cudaEventDestroy(p->ps.ev);
+    if (p->ps.ctl) cudaFreeHost(p->ps.ctl);
+    if (p->ps.d_relay) cudaFree(p->ps.d_relay);
     // unlink: a neighbour that outlives this stage must not forward into (or be unlinked from) freed memory
     if (p->upstream) p->upstream->downstream = nullptr;
     if (p->downstream) p->downstream->upstream = nullptr;
@@ -667,6 +825,7 @@ int sdr_pipe_push(sdr_pipe_t *p, const void *in, long long n, int mem) {
 
 int sdr_pipe_ready(sdr_pipe_t *p, int *n_blocks) {
     if (!p || !n_blocks) return set_error(SDR_EINVAL, "sdr_pipe_ready: bad argument");
+    persist_poll(p);
     if (is_fir_kind(p->kind)) *n_blocks = (int)((long long)(p->fifo.size() / p->out_eb) / p->block_out);
     else *n_blocks = (int)p->vec_lens.size();
     return SDR_OK;
@@ -674,6 +833,7 @@ int sdr_pipe_ready(sdr_pipe_t *p, int *n_blocks) {
 
 int sdr_pipe_next_len(sdr_pipe_t *p, long long *n) {
     if (!p || !n) return set_error(SDR_EINVAL, "sdr_pipe_next_len: bad argument");
+    persist_poll(p);
     if (is_fir_kind(p->kind)) {
         if ((long long)(p->fifo.size() / p->out_eb) < p->block_out) return set_error(SDR_EAGAIN, "sdr_pipe_next_len: no complete output block yet");
         *n = p->block_out;
@@ -686,6 +846,7 @@ int sdr_pipe_next_len(sdr_pipe_t *p, long long *n) {
 
 int sdr_pipe_pop(sdr_pipe_t *p, void *out, long long *n_out, int mem) {
     if (!p || !out || mem < SDR_HOST || mem > SDR_HOST_PINNED) return set_error(SDR_EINVAL, "sdr_pipe_pop: bad argument");
+    persist_poll(p);
     long long n;
     if (is_fir_kind(p->kind)) {
         n = p->block_out;
@@ -711,10 +872,26 @@ int sdr_pipe_sync(sdr_pipe_t *p) {
     if (!p) return set_error(SDR_EINVAL, "sdr_pipe_sync: null handle");
     SDR_TRY(p->ctx->bind());
     SDR_TRY(flush_pending(p));
+    if (p->ps.open) { SDR_TRY(persist_close(p)); SDR_TRY(process_fir(p, true)); SDR_TRY(forward(p)); }
     SDR_TRY(materialize_ext(p));   // SDR_DEVICE_HELD vectors are the caller's again after this call
     SDR_CUDA(cudaStreamSynchronize(p->ctx->stream));
     SDR_CUDA(cudaStreamSynchronize(p->ctx->side));
     trace_dump();
+    return SDR_OK;
+}
+
+// Per-vector device pushes without a launch per vector: SDR_DEVICE_HELD vectors pushed back to back (adjacent in memory)
+// are consumed by a RESIDENT kernel that polls how far the stream has been published and publishes the runs it has
+// finished (kernels_fast.cu: k_dec_ring_persist).  max_session_samples bounds one session (the output FIFO is sized for
+// it up front); 0 switches the mode off.  Complex decimators with 65..128 stored taps and decimation 8 only.
+int sdr_pipe_set_persistent(sdr_pipe_t *p, long long max_session_samples) {
+    if (!p || max_session_samples < 0) return set_error(SDR_EINVAL, "sdr_pipe_set_persistent: bad argument");
+    if (max_session_samples > 0 && !(p->kind == P_DECIM && p->fir->cplx && p->fir->D == 8 && p->fir->T > 64 && p->fir->T <= 128 &&
+                                     p->fir->arith == SDR_ARITH_FAST))
+        return set_error(SDR_EINVAL, "sdr_pipe_set_persistent: no persistent consumer for this stage (complex decimate-by-8, 65..128 taps)");
+    SDR_TRY(p->ctx->bind());
+    SDR_TRY(persist_close(p));
+    p->persist_max = max_session_samples;
     return SDR_OK;
 }
 
@@ -724,6 +901,7 @@ int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs) {
     if (is_fir_kind(p->kind) && min_outputs > 0) {
         // size both buffers for the batch once, instead of growing by doubling while the stream runs
         SDR_TRY(p->ctx->bind());
+        SDR_TRY(persist_close(p));
         SDR_TRY(flush_pending(p));    // a reserve may slide or reallocate: no deferred copy may still target the old place,
         SDR_TRY(fifo_writable(p));    // and no in-flight drain may still be reading it
         long long in_per_out = is_resamp_kind(p->kind) ? (p->res->M + p->res->L - 1) / p->res->L
@@ -781,6 +959,7 @@ int sdr_pipe_state_save(sdr_pipe_t *p, void *buf, size_t capacity, size_t *writt
     if (!p || !buf) return set_error(SDR_EINVAL, "sdr_pipe_state_save: bad argument");
     SDR_TRY(p->ctx->bind());
     SDR_TRY(flush_pending(p));
+    SDR_TRY(persist_close(p));
     SDR_TRY(materialize_ext(p));
     SDR_TRY(fifo_writable(p));
     StateHeader h;
@@ -846,8 +1025,12 @@ int sdr_pipe_state_restore(sdr_pipe_t *p, const void *buf, size_t bytes) {
 // pop every complete vector of `sink` into out[written...] with ONE copy (FIR kinds) / one copy per vector otherwise
 static int drain(sdr_pipe *sink, void *out, long long out_capacity, int out_mem, long long *written) {
     if (is_fir_kind(sink->kind)) {
+        persist_poll(sink);
         long long nb = (long long)(sink->fifo.size() / sink->out_eb) / sink->block_out;
         if (nb == 0) return SDR_OK;
+        // while a persistent consumer is resident, hand its outputs over in pieces of >= 32 vectors: a copy per vector would
+        // cost more host time than the vector takes to compute (the session's end drains the rest)
+        if (sink->ps.open && nb < 32) return SDR_OK;
         long long n = nb * sink->block_out;
         if (*written + n > out_capacity) return set_error(SDR_EINVAL, "sdr_pipe_run: output capacity %lld too small", out_capacity);
         TraceScope tr("drain", sink->ctx, n);

@@ -231,6 +231,10 @@ class NativePipe:
     def sync(self):
         L.check(L.lib.sdr_pipe_sync(self.h))
 
+    def set_persistent(self, max_session_samples):
+        """consume held device vectors with a resident kernel instead of launches (sdr_pipe_set_persistent)"""
+        L.check(L.lib.sdr_pipe_set_persistent(self.h, max_session_samples))
+
     def ready(self):
         n = C.c_int()
         L.check(L.lib.sdr_pipe_ready(self.h, C.byref(n)))

@@ -1,0 +1,139 @@
+"""Persistent consumer (sdr_pipe_set_persistent): SDR_DEVICE_HELD vectors pushed one by one are consumed by a resident kernel
+that polls a flag-published stream -- the per-8192 contract of firDecimator (Filter.hs:578-598) without a launch per vector.
+The yielded stream must be bit-identical to the ordinary launch path: sessions that roll over their capacity, a stream
+that stalls (request / response: more input only after the outputs so far have been popped), vectors that are not adjacent,
+ragged vector sizes."""
+import time
+
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
+
+
+@pytest.fixture(scope="module")
+def sdr():
+    import sdr_b200
+    assert sdr_b200.has_cuda()
+    return sdr_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(sdr):
+    return sdr.default_context()
+
+
+def _drain(pipe, out):
+    while pipe.ready():
+        out.append(pipe.pop())
+
+
+def _reference(sdr, taps, x, sizes, block):
+    p = sdr.pipeFirDecimator(sdr.cudaDecimatorC(8, taps, sizeMultiple=4), block)
+    want, o = [], 0
+    for n in sizes:
+        p.push(x[o:o + n])
+        _drain(p, want)
+        o += n
+    p.close()
+    return want
+
+
+@pytest.mark.parametrize("sizes,max_session", [
+    ([8192] * 300, 1 << 24),                                  # one session
+    ([8192] * 6000, 1 << 26),                                 # ~10 runs per CTA: the ring flows across runs
+    ([8192] * 300, 1 << 18),                                  # capacity roll-over: many sessions
+    ([8192, 3000, 8192 * 5, 16384, 130, 8192 * 40, 8192] * 3, 1 << 22),   # ragged vector sizes
+])
+def test_persistent_consumer_equals_launch_path(sdr, ctx, sizes, max_session):
+    taps = synth.windowed_sinc_taps(128, 1 / 16)
+    x = synth.noise_complex(sum(sizes), first=99)
+    want = _reference(sdr, taps, x, sizes, 1024)
+    d = sdr.cudaDecimatorC(8, taps, sizeMultiple=4)
+    p = sdr.pipeFirDecimator(d, 1024)
+    p.set_persistent(max_session)
+    dbuf = ctx.to_device(x)
+    got, o, saw = [], 0, False
+    for n in sizes:
+        p.push_device(dbuf.at(8 * o), n, held=True)
+        saw |= d.last_kernel().startswith("dec_c_ring_persist")
+        _drain(p, got)
+        o += n
+    p.sync()
+    _drain(p, got)
+    p.close()
+    dbuf.free()
+    assert saw, d.last_kernel()
+    assert len(got) == len(want) and len(want) > 0
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_persistent_consumer_request_response_does_not_stall(sdr, ctx):
+    """the producer only sends more once it has SEEN the outputs of what it sent: every published run must be computed
+    without anything further being published"""
+    taps = synth.windowed_sinc_taps(128, 1 / 16)
+    nvec = 99
+    x = synth.noise_complex(8192 * nvec, first=7)
+    want = np.concatenate(_reference(sdr, taps, x, [8192] * nvec, 1024))
+    d = sdr.cudaDecimatorC(8, taps, sizeMultiple=4)
+    p = sdr.pipeFirDecimator(d, 1024)
+    p.set_persistent(1 << 22)
+    dbuf = ctx.to_device(x)
+    got, pushed = [], 0
+    while pushed < nvec:
+        for _ in range(11):                     # eleven vectors: one run (8 vectors + halo) completes, the second cannot
+            if pushed < nvec:
+                p.push_device(dbuf.at(8 * 8192 * pushed), 8192, held=True)
+                pushed += 1
+        # outputs of every complete run must appear although nothing more is published
+        runs = (pushed * 8192 - 128) // 65536
+        expect_blocks = runs * 8
+        t0 = time.time()
+        while len(got) < expect_blocks:
+            _drain(p, got)
+            assert time.time() - t0 < 20, (len(got), expect_blocks, pushed)
+    p.sync()
+    _drain(p, got)
+    p.close()
+    dbuf.free()
+    y = np.concatenate(got)
+    assert len(y) == len(want) and np.array_equal(y.view(np.uint32), want.view(np.uint32))
+
+
+def test_persistent_consumer_non_adjacent_vectors_and_downstream(sdr, ctx):
+    """a vector somewhere else in memory ends the session (the ordinary path bridges), and a connected stage is fed"""
+    taps = synth.windowed_sinc_taps(128, 1 / 16)
+    sizes = [8192] * 40
+    x = synth.noise_complex(sum(sizes), first=1)
+    # reference: decimator >-> fmDemod, host pushes
+    p0 = sdr.pipeFirDecimator(sdr.cudaDecimatorC(8, taps, sizeMultiple=4), 1024)
+    p1 = sdr.pipeFmDemod()
+    p0.connect(p1)
+    want = []
+    for i, n in enumerate(sizes):
+        p0.push(x[8192 * i:8192 * (i + 1)])
+        _drain(p1, want)
+    p0.close(); p1.close()
+    # vectors 0..19 adjacent, a 4 KiB hole, vectors 20..39 adjacent
+    d = sdr.cudaDecimatorC(8, taps, sizeMultiple=4)
+    q0 = sdr.pipeFirDecimator(d, 1024)
+    q1 = sdr.pipeFmDemod()
+    q0.connect(q1)
+    q0.set_persistent(1 << 22)
+    dbuf = ctx.alloc(x.nbytes + 4096 + 64)
+    dbuf.upload(x[:8192 * 20])
+    dbuf.upload(x[8192 * 20:], offset_bytes=8 * 8192 * 20 + 4096)
+    got = []
+    for i in range(40):
+        off = 8 * 8192 * i + (4096 if i >= 20 else 0)
+        q0.push_device(dbuf.at(off), 8192, held=True)
+        _drain(q1, got)
+    q0.sync()
+    _drain(q1, got)
+    q0.close(); q1.close()
+    dbuf.free()
+    a, b = np.concatenate(got), np.concatenate(want)
+    assert len(a) == len(b) and np.array_equal(a.view(np.uint32), b.view(np.uint32))
