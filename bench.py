@@ -43,8 +43,13 @@ ALGO_BYTES_PER_SAMPLE = 8.0 + 8.0 / FACTOR   # each inpu
 
 
 def design_taps():
-    import synth
-    return synth.windowed_sinc_taps(TAPS, 1.0 / (2 * FACTOR))
+    """the package's tap designer (sdr_b200/filterdesign.py: the Hamming-windowed sinc of SDR.FilterDesign), loaded by path so
+    that the reference arm does not need the native library"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_sdr_b200_filterdesign", os.path.join(ROOT, "sdr_b200", "filterdesign.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.windowed_sinc_taps(TAPS, 1.0 / (2 * FACTOR))
 
 
 def measured_peak():
