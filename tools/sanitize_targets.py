@@ -81,6 +81,32 @@ def main():
             assert n_out.value > 0
             done.append(L.lib.sdr_pipe_last_kernel(p.h).decode())
             p.close()
+    # fused low-rate end behind the fused front end (two-stage FM chain), ragged in-place pushes
+    half = sdr_b200.windowed_sinc_taps(64, 1 / 4)[:32]
+    rr = sdr_b200.cudaResamplerR(3, 10, sdr_b200.windowed_sinc_taps(90, 1 / 20, gain=3.0), ctx=ctx, sizeMultiple=8)
+    ff = sdr_b200.cudaFilterSymR(half, ctx=ctx)
+    fe, lo = sdr_b200.pipeFmFrontEnd(d, 1000), sdr_b200.pipeFmLowRate(rr, 1000, ff, 500, 0.2)
+    fe.connect(lo)
+    L.check(L.lib.sdr_pipe_run(fe.h, lo.h, raw.ptr, 2 * 8192 * 7 + 2 * 3, (2 * n) // (2 * 8192 * 7 + 6), L.SDR_DEVICE_HELD, y.ptr, n, L.SDR_DEVICE,
+                               C.byref(n_out)))
+    assert n_out.value > 0
+    done.append(L.lib.sdr_pipe_last_kernel(lo.h).decode())
+    fe.close(); lo.close()
+    # in-place pushes through every ring family (two-segment launches, bridge launches)
+    for mk in (lambda: sdr_b200.pipeFirDecimator(d, 1024), lambda: sdr_b200.pipeFirFilter(sdr_b200.cudaFilterC(sdr_b200.windowed_sinc_taps(32, 1 / 4), ctx=ctx, sizeMultiple=8), 4096)):
+        p = mk()
+        L.check(L.lib.sdr_pipe_run(p.h, p.h, x.ptr, 8192 + 3 * 2, n // (8192 + 6), L.SDR_DEVICE_HELD, y.ptr, n, L.SDR_DEVICE, C.byref(n_out)))
+        assert n_out.value > 0
+        p.close()
+    done.append("held pushes")
+    # persistent consumer: up to 40 vectors (5 runs on 5 CTAs) + the ordinary launch for what the session leaves
+    p = sdr_b200.pipeFirDecimator(d, 1024)
+    L.check(L.lib.sdr_pipe_set_persistent(p.h, 1 << 22))
+    nv = min(40, n // 8192)
+    L.check(L.lib.sdr_pipe_run(p.h, p.h, x.ptr, 8192, nv, L.SDR_DEVICE_HELD, y.ptr, n, L.SDR_DEVICE, C.byref(n_out)))
+    L.check(L.lib.sdr_pipe_run(p.h, p.h, x.ptr, 8192, nv, L.SDR_DEVICE, y2.ptr, n, L.SDR_DEVICE, C.byref(n_out)))   # same vectors, copied
+    p.close()
+    done.append("persistent consumer")
     # dcBlocker, chunk-parallel
     d_fin = ctx.alloc(8)
     ctx.dc_tuning(0, -1, -1, 1 << 16)
