@@ -322,8 +322,8 @@ int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs);
  * a RESIDENT kernel -- a push is one store into a page-locked control block the kernel polls, sdr_pipe_ready / _pop see the
  * runs it has published as finished.  A session ends at sdr_pipe_sync, at a vector that is not adjacent, or after
  * max_session_samples (the output FIFO is sized for that up front); the ordinary launch path finishes what a session leaves
- * (the carried tail, an incomplete run).  The kernel leaves 8 SMs free; a warp that waits > 3 s for input abandons the session
- * with an error instead of hanging the GPU.  Complex decimate-by-8 stages with 65..128 stored taps only; 0 switches it off. */
+ * (the carried tail, an incomplete run).  The kernel leaves 7 SMs free; after 3 s without input it winds the session down
+ * without hanging the GPU (the next push opens a new session).  Complex decimate-by-8 stages with up to 128 stored taps; 0 switches it off. */
 int sdr_pipe_set_persistent(sdr_pipe_t *p, long long max_session_samples);
 /* `runEffect $ each vectors >-> p >-> ... >-> sink >-> collect` as one native loop: pushes n_vecs consecutive vectors of
  * vec_len input elements starting at `in` into `p`, pops every vector `sink` yields (sink = p, or the last stage

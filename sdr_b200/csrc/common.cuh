@@ -98,9 +98,9 @@ Ctx *default_ctx(int *status);   // per-thread context behind the reference-sign
 int launch_dec_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_taps, Seg2 seg, void *d_out, long long num,
                     long long *done, const char **name);
 // persistent consumer (kernels_fast.cu): see PersistCtl there; ctl = page-locked mapped control block
+bool dec_persist_geometry(int taps_stored, int D, bool cplx, int *run_samples, int *halo_samples);
 int launch_dec_persist(Ctx *c, int taps_stored, int D, bool cplx, const float *d_taps, const void *d_in, void *d_out, void *ctl,
-                       void *d_relay, long long runs_total, cudaStream_t stream, int *run_samples, int *halo_samples, int *grid_out,
-                       const char **name);
+                       void *d_relay, long long runs_total, cudaStream_t stream, int *grid_out, const char **name);
 bool dec_fast_will_cover(bool cplx, int taps_stored, int D, Seg2 seg, long long num);
 // opt a kernel in to `smem_bytes` of dynamic shared memory, once per (kernel, device)
 int ring_attr(Ctx *c, const void *kernel, int smem_bytes);

@@ -307,18 +307,18 @@ int launch_dec_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_ta
     SDR_RING(true, 128, 8, 8, "dec_c_ring<128,8,8>")
     SDR_RING(true, 64, 8, 8, "dec_c_ring<64,8,8>")
     SDR_RING(true, 32, 8, 8, "dec_c_ring<32,8,8>")
-    SDR_RING(true, 128, 4, 8, "dec_c_ring<128,4,8>")
-    SDR_RING(true, 64, 4, 8, "dec_c_ring<64,4,8>")
-    SDR_RING(true, 32, 4, 8, "dec_c_ring<32,4,8>")
+    SDR_RING(true, 128, 4, 16, "dec_c_ring<128,4,16>")
+    SDR_RING(true, 64, 4, 16, "dec_c_ring<64,4,16>")
+    SDR_RING(true, 32, 4, 16, "dec_c_ring<32,4,16>")
     SDR_RING(true, 128, 16, 4, "dec_c_ring<128,16,4>")
     SDR_RING(true, 64, 16, 4, "dec_c_ring<64,16,4>")
     SDR_RING(true, 32, 16, 4, "dec_c_ring<32,16,4>")
     SDR_RING(false, 128, 8, 16, "dec_r_ring<128,8,16>")
     SDR_RING(false, 64, 8, 16, "dec_r_ring<64,8,16>")
     SDR_RING(false, 32, 8, 16, "dec_r_ring<32,8,16>")
-    SDR_RING(false, 128, 4, 16, "dec_r_ring<128,4,16>")
-    SDR_RING(false, 64, 4, 16, "dec_r_ring<64,4,16>")
-    SDR_RING(false, 32, 4, 16, "dec_r_ring<32,4,16>")
+    SDR_RING(false, 128, 4, 32, "dec_r_ring<128,4,32>")
+    SDR_RING(false, 64, 4, 32, "dec_r_ring<64,4,32>")
+    SDR_RING(false, 32, 4, 32, "dec_r_ring<32,4,32>")
     SDR_RING(false, 128, 16, 8, "dec_r_ring<128,16,8>")
     SDR_RING(false, 64, 16, 8, "dec_r_ring<64,16,8>")
     SDR_RING(false, 32, 16, 8, "dec_r_ring<32,16,8>")
@@ -558,26 +558,41 @@ k_dec_ring_persist(const void *__restrict__ in, void *__restrict__ out, const fl
     publish_pending();
 }
 
-// launches the persistent consumer on `stream` over the contiguous device stream at d_in; grid = SMs - reserve
+// geometry of the persistent consumer that serves a shape: samples per run and halo samples behind a run; false: none
+bool dec_persist_geometry(int taps_stored, int D, bool cplx, int *run_samples, int *halo_samples) {
+    if (!cplx || D != 8 || taps_stored > 128 || taps_stored < 1) return false;
+    *run_samples = 32 * 256 * 8;
+    *halo_samples = taps_stored <= 32 ? RingCfg<true, 32, 8, 8>::HALO_SEGS * 64
+                  : taps_stored <= 64 ? RingCfg<true, 64, 8, 8>::HALO_SEGS * 64 : RingCfg<true, 128, 8, 8>::HALO_SEGS * 64;
+    return true;
+}
+
+template <int T>
+static int launch_persist_t(Ctx *c, const float *d_taps, const void *d_in, void *d_out, void *ctl, void *d_relay, long long runs_total,
+                            cudaStream_t stream, int grid) {
+    typedef RingCfg<true, T, 8, 8> C;
+    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_ring_persist<true, T, 8, 8, 32>), C::SMEM_BYTES));
+    k_dec_ring_persist<true, T, 8, 8, 32><<<grid + 1, 256, C::SMEM_BYTES, stream>>>(d_in, d_out, d_taps, (PersistCtl *)ctl,
+                                                                                     (PersistRelay *)d_relay, runs_total);
+    return SDR_OK;
+}
+
+// launches the persistent consumer on `stream` over the contiguous device stream at d_in: grid = SMs - 8 worker CTAs (the
+// remaining SMs stay free for whatever else the process launches while the consumer is resident) + 1 relay CTA.  A run =
+// 32 sub-tiles = 8192 outputs = one yielded vector of the headline configuration.
 int launch_dec_persist(Ctx *c, int taps_stored, int D, bool cplx, const float *d_taps, const void *d_in, void *d_out, void *ctl,
-                       void *d_relay, long long runs_total, cudaStream_t stream, int *run_samples, int *halo_samples, int *grid_out,
-                       const char **name) {
+                       void *d_relay, long long runs_total, cudaStream_t stream, int *grid_out, const char **name) {
     *name = "none";
-    if (!cplx || D != 8 || taps_stored > 128 || taps_stored <= 64) return set_error(SDR_EINVAL, "no persistent kernel for this shape");
-    typedef RingCfg<true, 128, 8, 8> C;
-    constexpr int PB = 32;          // a run = 32 sub-tiles = 8192 outputs = one yielded vector of the headline configuration
+    int rs, hs;
+    if (!dec_persist_geometry(taps_stored, D, cplx, &rs, &hs)) return set_error(SDR_EINVAL, "no persistent kernel for this shape");
     SDR_TRY(c->bind());
-    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_ring_persist<true, 128, 8, 8, PB>), C::SMEM_BYTES));
-    int grid = c->sm_count - 8;     // worker CTAs; one more CTA relays the control block; the remaining SMs stay free for
-                                    // whatever else the process launches while the consumer is resident
+    int grid = c->sm_count - 8;
     if (grid < 1) grid = 1;
-    *run_samples = PB * C::SUB_OUT * 8;
-    *halo_samples = C::HALO_SEGS * C::SEG_ELEMS;
     *grid_out = grid;
-    *name = "dec_c_ring_persist<128,8,8,32>";
     SDR_CUDA(cudaMemsetAsync(d_relay, 0, sizeof(PersistRelay), stream));
-    k_dec_ring_persist<true, 128, 8, 8, PB><<<grid + 1, 256, C::SMEM_BYTES, stream>>>(d_in, d_out, d_taps, (PersistCtl *)ctl,
-                                                                                       (PersistRelay *)d_relay, runs_total);
+    if (taps_stored <= 32)      { *name = "dec_c_ring_persist<32,8,8,32>";  SDR_TRY(launch_persist_t<32>(c, d_taps, d_in, d_out, ctl, d_relay, runs_total, stream, grid)); }
+    else if (taps_stored <= 64) { *name = "dec_c_ring_persist<64,8,8,32>";  SDR_TRY(launch_persist_t<64>(c, d_taps, d_in, d_out, ctl, d_relay, runs_total, stream, grid)); }
+    else                        { *name = "dec_c_ring_persist<128,8,8,32>"; SDR_TRY(launch_persist_t<128>(c, d_taps, d_in, d_out, ctl, d_relay, runs_total, stream, grid)); }
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     return SDR_OK;

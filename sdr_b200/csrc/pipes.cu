@@ -291,8 +291,8 @@ static int persist_try(sdr_pipe *p, bool *taken) {
             SDR_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
             SDR_CUDA(cudaEventCreateWithFlags(&S.ev, cudaEventDisableTiming));
         }
-        // geometry of the kernel that will serve the shape (also validates the shape)
-        S.run_samples = 32 * 256 * f.D; S.halo_samples = 128;   // checked against the launcher below
+        // geometry of the kernel that will serve the shape
+        if (!dec_persist_geometry(f.T, f.D, f.cplx, &S.run_samples, &S.halo_samples)) return SDR_OK;
         const long long max_samples = p->persist_max;
         const long long out_bytes = (max_samples / f.D + 1) * (long long)p->out_eb;
         SDR_TRY(p->fifo.reserve((size_t)out_bytes));
@@ -315,10 +315,8 @@ static int persist_try(sdr_pipe *p, bool *taken) {
         // everything enqueued on the ctx stream so far (what produced the FIFO's contents, tail copies) precedes the consumer
         SDR_CUDA(cudaEventRecord(S.ev, p->ctx->stream));
         SDR_CUDA(cudaStreamWaitEvent(S.stream, S.ev, 0));
-        int rs = 0, hs = 0;
         SDR_TRY(launch_dec_persist(p->ctx, f.T, f.D, f.cplx, f.d_taps, S.base, p->fifo.p + S.fifo_base, d_ctl, S.d_relay, runs_total, S.stream,
-                                   &rs, &hs, &S.grid, &S.kernel));
-        if (rs != S.run_samples || hs != S.halo_samples) return set_error(SDR_EINVAL, "persistent consumer: geometry mismatch");
+                                   &S.grid, &S.kernel));
         p->fifo.fixed = true;
         S.open = true;
         f.last_kernel = S.kernel;
@@ -883,12 +881,13 @@ int sdr_pipe_sync(sdr_pipe_t *p) {
 // Per-vector device pushes without a launch per vector: SDR_DEVICE_HELD vectors pushed back to back (adjacent in memory)
 // are consumed by a RESIDENT kernel that polls how far the stream has been published and publishes the runs it has
 // finished (kernels_fast.cu: k_dec_ring_persist).  max_session_samples bounds one session (the output FIFO is sized for
-// it up front); 0 switches the mode off.  Complex decimators with 65..128 stored taps and decimation 8 only.
+// it up front); 0 switches the mode off.  Complex decimators with up to 128 stored taps and decimation 8 only.
 int sdr_pipe_set_persistent(sdr_pipe_t *p, long long max_session_samples) {
     if (!p || max_session_samples < 0) return set_error(SDR_EINVAL, "sdr_pipe_set_persistent: bad argument");
-    if (max_session_samples > 0 && !(p->kind == P_DECIM && p->fir->cplx && p->fir->D == 8 && p->fir->T > 64 && p->fir->T <= 128 &&
-                                     p->fir->arith == SDR_ARITH_FAST))
-        return set_error(SDR_EINVAL, "sdr_pipe_set_persistent: no persistent consumer for this stage (complex decimate-by-8, 65..128 taps)");
+    int rs, hs;
+    if (max_session_samples > 0 && !(p->kind == P_DECIM && p->fir->arith == SDR_ARITH_FAST &&
+                                     dec_persist_geometry(p->fir->T, p->fir->D, p->fir->cplx, &rs, &hs)))
+        return set_error(SDR_EINVAL, "sdr_pipe_set_persistent: no persistent consumer for this stage (complex decimate-by-8, up to 128 taps)");
     SDR_TRY(p->ctx->bind());
     SDR_TRY(persist_close(p));
     p->persist_max = max_session_samples;

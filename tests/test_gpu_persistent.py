@@ -71,6 +71,32 @@ def test_persistent_consumer_equals_launch_path(sdr, ctx, sizes, max_session):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def test_persistent_consumer_fm_example_decimator(sdr, ctx):
+    """the FM example's 51-tap RF decimator (examples/fm/Coeffs.hs:11-66) on the 64-tap-capacity persistent kernel"""
+    import os
+    fm = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fm_example_coeffs.npz"))
+    taps = fm["coeffsRFDecim"]
+    sizes = [8192] * 2500
+    x = synth.noise_complex(sum(sizes), first=5)
+    want = np.concatenate(_reference(sdr, taps, x, sizes, 8192))
+    d = sdr.cudaDecimatorC(8, taps, sizeMultiple=4)
+    p = sdr.pipeFirDecimator(d, 8192)
+    p.set_persistent(1 << 25)
+    dbuf = ctx.to_device(x)
+    got, saw = [], False
+    for i in range(len(sizes)):
+        p.push_device(dbuf.at(8 * 8192 * i), 8192, held=True)
+        saw |= d.last_kernel() == "dec_c_ring_persist<64,8,8,32>"
+        if i % 64 == 0:
+            _drain(p, got)
+    p.sync()
+    _drain(p, got)
+    p.close()
+    dbuf.free()
+    y = np.concatenate(got)
+    assert saw and len(y) == len(want) and np.array_equal(y.view(np.uint32), want.view(np.uint32))
+
+
 def test_persistent_consumer_request_response_does_not_stall(sdr, ctx):
     """the producer only sends more once it has SEEN the outputs of what it sent: every published run must be computed
     without anything further being published"""
