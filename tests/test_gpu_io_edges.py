@@ -155,3 +155,44 @@ def test_udp_source_and_sink(sdr):
         assert np.array_equal(d.view(np.uint32), w.view(np.uint32))
     for s in (rx, back, out, tx):
         s.close()
+
+
+@pytest.mark.parametrize("flag", [[], ["--reference-coeffs"]])
+def test_fm_receiver_example_end_to_end(tmp_path, flag):
+    """examples/fm_receiver.py (the reference's examples/fm/fm.hs on the device, two fused stages, file in / file out) ==
+    the six stages of fm.hs:34-40 pushed one after the other from host vectors, bit for bit; with the BASELINE shapes and
+    with the reference example's own coefficient sets"""
+    import subprocess
+    import sys
+    import sdr_b200
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rng = np.random.default_rng(21)
+    n_vec = 700
+    raw = rng.integers(0, 256, 16384 * n_vec, dtype=np.uint8)
+    fin, fout = tmp_path / "iq.u8", tmp_path / "audio.f32"
+    raw.tofile(fin)
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "fm_receiver.py"), str(fin), str(fout)] + flag,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = np.fromfile(fout, np.float32)
+    if flag:
+        fm = np.load(os.path.join(root, "tests", "golden", "fm_example_coeffs.npz"))
+        c_rf, c_rs, c_au = fm["coeffsRFDecim"], fm["coeffsAudioResampler"], fm["coeffsAudioFilter"]
+    else:
+        w = sdr_b200.windowed_sinc_taps
+        c_rf, c_rs, c_au = w(128, 1 / 16), w(90, 1 / 20, gain=3.0), w(64, 1 / 4)[:32]
+    q = [sdr_b200.pipeConvertU8(), sdr_b200.pipeFirDecimator(sdr_b200.cudaDecimatorC(8, c_rf, sizeMultiple=4), 8192), sdr_b200.pipeFmDemod(),
+         sdr_b200.pipeFirResampler(sdr_b200.cudaResamplerR(3, 10, c_rs, sizeMultiple=8), 8192),
+         sdr_b200.pipeFirFilter(sdr_b200.cudaFilterSymR(c_au), 8192), sdr_b200.pipeScale(0.2)]
+    for a, b in zip(q, q[1:]):
+        a.connect(b)
+    want = []
+    for i in range(n_vec):
+        q[0].push(raw[16384 * i:16384 * (i + 1)])
+        while q[-1].ready():
+            want.append(q[-1].pop())
+    want = np.concatenate(want)
+    for p in q:
+        p.close()
+    assert len(got) == len(want) and len(got) >= 8192 * 20
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
