@@ -48,10 +48,23 @@ struct FirRCfg {
     static_assert(NS >= 11, "ring too small for 8 warps plus prefetch");
 };
 
-template <bool CPLX, int T, int D, int R, int S>
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
+// PAIR (real data, D = 1): two ADJACENT OUTPUTS share one FFMA2 -- (y[2p], y[2p+1]) += c[k] * (x[2p+k], x[2p+k+1]) -- so every
+// output still sums its taps in increasing order (bit-identical to the scalar form and to the generic kernel) while the
+// FP32 instructions halve: the scalar kernel sits at the scalar-FFMA issue peak (59.7 TFLOP/s measured, profiles/r01_mb_fma.txt),
+// FFMA2 reaches 67.  Sample pairs that start at an even index come straight out of the LDS.128 registers, the odd ones cost
+// a register move each.
+template <bool CPLX, int T, int D, int R, int S, bool PAIR = false>
 __global__ void __launch_bounds__(256, 1)
 k_fir_ring(const void *__restrict__ in_v, void *__restrict__ out_v, const float *__restrict__ taps, long long n_slots) {
     typedef FirRCfg<CPLX, T, D, R, S> C;
+    static_assert(!PAIR || (!CPLX && D == 1 && R % 4 == 0), "output pairing is the real stride-1 form");
     // widest store a lane's R outputs allow (compile time) and the output pointer permits (run time): ONE vector variant
     // plus the scalar one per instantiation, so the compiler clones the unrolled loop body only twice
     constexpr bool CAN16 = (R * C::EB) % 16 == 0;
@@ -101,6 +114,39 @@ k_fir_ring(const void *__restrict__ in_v, void *__restrict__ out_v, const float 
                 } else {
 #pragma unroll
                     for (int r = 0; r < R; r++) os[r] = acc[r];
+                }
+            } else if (PAIR) {
+                u64 acc2[R / 2];
+#pragma unroll
+                for (int p2 = 0; p2 < R / 2; p2++) acc2[p2] = 0ULL;
+                float carry = 0.0f;   // x[4 c4 - 1]
+#pragma unroll
+                for (int c4 = 0; c4 < C::NCH; c4++) {
+                    const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(w)[c4];   // (x0, x1), (x2, x3)
+                    float x0, x1, x2, x3;
+                    unpack2(v.x, x0, x1);
+                    unpack2(v.y, x2, x3);
+                    const u64 pr[4] = {pack2(carry, x0), v.x, pack2(x1, x2), v.y};       // pairs starting at 4 c4 - 1, 4 c4, 4 c4 + 1, 4 c4 + 2
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int s0 = 4 * c4 - 1 + i;                                   // index of the pair's first sample
+                        if (s0 < 0) continue;
+#pragma unroll
+                        for (int p2 = 0; p2 < R / 2; p2++) {
+                            const int k = s0 - 2 * p2;
+                            if (k >= 0 && k < T) acc2[p2] = ffma2(pr[i], dup2(tap[k < 0 ? 0 : (k >= T ? 0 : k)]), acc2[p2]);
+                        }
+                    }
+                    carry = x3;
+                }
+                float *os = reinterpret_cast<float *>(out_v) + o0;
+                if (CAN16 && vec_store) {
+                    ulonglong2 *o = reinterpret_cast<ulonglong2 *>(os);
+#pragma unroll
+                    for (int p2 = 0; p2 + 1 < R / 2; p2 += 2) o[p2 / 2] = make_ulonglong2(acc2[p2], acc2[p2 + 1]);
+                } else {
+#pragma unroll
+                    for (int p2 = 0; p2 < R / 2; p2++) { float a, b; unpack2(acc2[p2], a, b); os[2 * p2] = a; os[2 * p2 + 1] = b; }
                 }
             } else {
                 float acc[R];
@@ -191,10 +237,10 @@ k_fir_r_ffa_ring(const void *__restrict__ in_v, void *__restrict__ out_v, const 
     }
 }
 
-template <bool CPLX, int T, int D, int R, int S, bool FFA = false>
+template <bool CPLX, int T, int D, int R, int S, bool FFA = false, bool PAIR = false>
 static int launch_fir_b(Ctx *c, const float *d_taps, const void *d_in, long long n_in, void *d_out, long long num, long long *done) {
     typedef FirRCfg<CPLX, T, D, R, S> C;
-    void (*kernel)(const void *, void *, const float *, long long) = k_fir_ring<CPLX, T, D, R, S>;
+    void (*kernel)(const void *, void *, const float *, long long) = k_fir_ring<CPLX, T, D, R, S, PAIR>;
     if constexpr (FFA) kernel = k_fir_r_ffa_ring<T, R, S>;
     long long n_slots = num / C::SLOT_OUT;
     long long by_in = (n_in - C::HALO) / C::SLOT_ELEMS;
@@ -227,6 +273,16 @@ int launch_fir_small_stride_fast(Ctx *c, bool cplx, int taps_stored, int D, cons
     if (ffa && T == 64) { *name = "fir_r_ffa_ring<64,20,6>"; return launch_fir_b<false, 64, 1, 20, 6, true>(c, d_taps, d_in, n_in, d_out, num, done); }
     if (ffa && T == 32) { *name = "fir_r_ffa_ring<32,20,6>"; return launch_fir_b<false, 32, 1, 20, 6, true>(c, d_taps, d_in, n_in, d_out, num, done); }
     if (ffa && T == 128) { *name = "fir_r_ffa_ring<128,20,6>"; return launch_fir_b<false, 128, 1, 20, 6, true>(c, d_taps, d_in, n_in, d_out, num, done); }
+    // 128-tap real stride-1 filter: two adjacent outputs per FFMA2 (same bits, half the FP32 instructions, 181 instead of 197
+    // registers): 202.6 vs 178 Gsamples/s.  With 64 / 32 taps the register moves that build the odd-aligned sample pairs cost
+    // more than the halved FMA issue saves (379 vs 465, 682 vs 704 Gsamples/s measured): those stay scalar.
+    // SDR_B200_FIR_PAIR=0 / =2 force the scalar / the paired form everywhere (measurement knob).
+    static const int pair_mode = getenv("SDR_B200_FIR_PAIR") ? atoi(getenv("SDR_B200_FIR_PAIR")) : 1;
+    if (pair_mode && !cplx && D == 1) {
+        if (T == 128) { *name = "fir_r_ring<128,20,6>"; return launch_fir_b<false, 128, 1, 20, 6, false, true>(c, d_taps, d_in, n_in, d_out, num, done); }
+        if (pair_mode == 2 && T == 64) { *name = "fir_r_ring<64,20,6>"; return launch_fir_b<false, 64, 1, 20, 6, false, true>(c, d_taps, d_in, n_in, d_out, num, done); }
+        if (pair_mode == 2 && T == 32) { *name = "fir_r_ring<32,20,6>"; return launch_fir_b<false, 32, 1, 20, 6, false, true>(c, d_taps, d_in, n_in, d_out, num, done); }
+    }
 #define SDR_FIRB(CP, TT, DD, RR, label)                                                     \
     if (cplx == CP && T == TT && D == DD) { *name = label; return launch_fir_b<CP, TT, DD, RR, 6>(c, d_taps, d_in, n_in, d_out, num, done); }
     SDR_FIRB(false, 64, 1, 20, "fir_r_ring<64,20,6>")

@@ -166,6 +166,7 @@ struct sdr_pipe {
     size_t ext_bytes = 0;
     long long block_r = 0;            // fused low-rate stage: the resampler stage's own vector length (its yields gate the filter)
     long long persist_max = 0;        // > 0: in-place runs are consumed by a persistent kernel, sessions of at most this many samples
+    int persist_idle_strikes = 0;     // consecutive sessions that wound down idle without finishing a single run
     PersistSession ps;
 };
 
@@ -262,6 +263,10 @@ static int persist_close(sdr_pipe *p) {
     // spinning kernel resident for ever).  Not a failure: the runs it did finish count, the rest is computed again.
     if (!h->error && S.runs_popped != (runs_final < S.runs_total ? runs_final : S.runs_total))
         return set_error(SDR_ECUDA, "persistent consumer: %lld runs completed, %lld expected", S.runs_popped, runs_final);
+    // Two sessions in a row that timed out without finishing a run: the host does not get to publish while the kernel is
+    // resident (e.g. a profiler that serialises launches) -- the mode cannot work there, the launch path takes over.
+    if (h->error && S.runs_popped == 0) { if (++p->persist_idle_strikes >= 2) p->persist_max = 0; }
+    else p->persist_idle_strikes = 0;
     consume_input(p, (size_t)S.runs_popped * (size_t)S.run_samples * p->in_eb);
     return SDR_OK;
 }
