@@ -163,3 +163,39 @@ def test_persistent_consumer_non_adjacent_vectors_and_downstream(sdr, ctx):
     dbuf.free()
     a, b = np.concatenate(got), np.concatenate(want)
     assert len(a) == len(b) and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_persistent_consumer_idle_wind_down_and_self_disable(sdr, ctx):
+    """a stream that stops for longer than the consumer's 3 s idle limit: the resident kernel winds down by itself, what it
+    left is computed by the ordinary launch path, and after two sessions in a row that finished nothing (a host that
+    cannot publish while the kernel is resident, e.g. under a serialising profiler) the stage stops opening sessions"""
+    taps = synth.windowed_sinc_taps(128, 1 / 16)
+    nvec = 60
+    x = synth.noise_complex(8192 * nvec, first=3)
+    want = np.concatenate(_reference(sdr, taps, x, [8192] * nvec, 1024))
+    d = sdr.cudaDecimatorC(8, taps, sizeMultiple=4)
+    p = sdr.pipeFirDecimator(d, 1024)
+    p.set_persistent(1 << 22)
+    dbuf = ctx.to_device(x)
+    got, pushed = [], 0
+
+    def push(k):
+        nonlocal pushed
+        for _ in range(k):
+            p.push_device(dbuf.at(8 * 8192 * pushed), 8192, held=True)
+            pushed += 1
+            _drain(p, got)
+
+    push(3)                       # less than one run: a session opens and starves
+    assert d.last_kernel().startswith("dec_c_ring_persist")
+    time.sleep(3.6)
+    push(3)                       # finds the session wound down (strike 1), a new one opens
+    time.sleep(3.6)
+    push(3)                       # strike 2: persistent mode is off from here on
+    push(nvec - pushed)
+    p.sync()
+    _drain(p, got)
+    p.close()
+    dbuf.free()
+    y = np.concatenate(got)
+    assert len(y) == len(want) and np.array_equal(y.view(np.uint32), want.view(np.uint32))
