@@ -116,14 +116,15 @@ int launch_res_fast(Ctx *c, bool cplx, int L, int M, int n_taps, const float *d_
 // (a_samples IQ pairs) followed by d_in_b, n_samples pairs in all (a_samples == n_samples: one segment).
 int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long a_samples,
                     const uint8_t *d_in_b, long long n_samples, float *d_out, long long num, float2 *d_bnd,
-                    long long bnd_capacity_subtiles, const float2 *d_carry, float2 *d_carry_out, long long *done, const char **name);
+                    long long bnd_capacity_subtiles, const float2 *d_carry, float2 *d_carry_out, unsigned int *d_ticket,
+                    long long *done, const char **name);
 // fused u8 convert + decimate (complex outputs), same kernel without the discriminator
 int launch_dec_u8(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long a_samples,
                   const uint8_t *d_in_b, long long n_samples, float *d_out, long long num, long long *done, const char **name);
 // firResampler >-> firFilter >-> P.map (* k) fused (kernels_lowrate.cu): outputs z[n], n in [n0, n0 + num), of the flat
 // stream z[n] = k * sum_t cf[t] r[n + t], r = the L/M resampling of x (taps cr); x = seg.a ++ seg.b and x[0] is the first
 // input sample of resampler output n0 (i.e. global sample ceil(n0 M / L)).  *done = num when a tuned kernel exists.
-int launch_fm_lowrate(Ctx *c, int L, int M, int n_taps_r, const float *d_taps_r, int n_taps_f, const float *d_taps_f, float scale,
+int launch_fm_lowrate(Ctx *c, int L, int M, int n_taps_r, const float *h_taps_r, int n_taps_f, const float *h_taps_f, float scale,
                       Seg2 seg, long long n0, float *d_out, long long num, long long *done, const char **name);
 
 }  // namespace sdr

@@ -15,13 +15,17 @@
 //   * epilogue: phase(y[m] * conj(y[m-1])) per output (demod.cuh); y[m-1] of a lane's first output comes from the
 //     previous lane by shuffle; the first output of a sub-tile needs the last output of the previous sub-tile, which
 //     another warp computes at another time: every sub-tile therefore also stores its first and last COMPLEX output
-//     (16 B per 2048 samples) and k_fm_front_fixup patches the 1-in-256 outputs afterwards.
+//     (16 B per 2048 samples) and the 1-in-256 outputs are patched at the end of the kernel -- the boundaries inside a
+//     CTA's own range by that CTA, the 147 boundaries between CTAs by whichever CTA takes the last ticket (fence +
+//     atomic counter: by then every other CTA's boundary samples are visible).  Round 1 used a second launch for this:
+//     3.4 us plus a launch gap behind every 39 us push.
 // The FIR sum order is the same as everywhere else, so fused == un-fused bit for bit (tests/test_gpu_parity.py).
 // Roofline: 2 B in + 0.5 B out per sample make HBM irrelevant; the kernel is FP32-pipe bound (1024 + 184 FFMA2 per pass).
 #include "demod.cuh"
 #include "ring_common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace sdr {
 
@@ -78,16 +82,18 @@ template <int T, int D, int R, int NW, bool SYM, bool DEMOD = true>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_t *__restrict__ in_b, long long n_chunks,
                 float *__restrict__ out, long long num,
-                float2 *__restrict__ bnd, float2 *__restrict__ carry_out, const float *__restrict__ taps, long long n_sub) {
+                float2 *__restrict__ bnd, float2 *__restrict__ carry_out, const float *__restrict__ taps, long long n_sub,
+                const float2 *__restrict__ carry_in, unsigned int *__restrict__ ticket) {
     typedef FmCfg<T, D, R, NW> C;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     long long q = n_sub / gridDim.x, rem = n_sub % gridDim.x;
     long long s0 = blockIdx.x * q + (blockIdx.x < rem ? blockIdx.x : rem);
-    int cnt = (int)(q + (blockIdx.x < rem ? 1 : 0));
-    if (cnt == 0) return;
+    int cnt = (int)(q + (blockIdx.x < rem ? 1 : 0));   // >= 1: the grid never exceeds the number of sub-tiles
 
+    // programmatic dependent launch, as in k_dec_ring: the next launch in the stream may be scheduled while this one drains
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t ring = smem_u32(smem);
     const uint32_t bar_full = ring + C::BAR_OFFSET;
     const uint32_t bar_empty = bar_full + C::NS * 8;
@@ -124,12 +130,14 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_
         cp_async_arrive(bar_full + 8 * slot);
     };
 
-    for (int u = warp; u < C::NS && u <= cnt; u += C::NWARPS) issue_fill(u);
-
     constexpr int NT = SYM ? T / 2 : T;
     float tap[NT];
 #pragma unroll
-    for (int k = 0; k < NT; k++) tap[k] = __ldg(taps + k);
+    for (int k = 0; k < NT; k++) tap[k] = __ldg(taps + k);   // written once when the record was made: safe before the wait
+    // everything before us in the stream has completed and flushed from here on (no-op without an early trigger)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    for (int u = warp; u < C::NS && u <= cnt; u += C::NWARPS) issue_fill(u);
     const u64 k_scale = dup2(0.0078125f), k_bias = dup2(-65537.0f);
 
     for (int u = warp; u < cnt; u += C::NWARPS) {
@@ -196,7 +204,7 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_
         prev.x = __shfl_up_sync(0xffffffffu, y[R - 1].x, 1);
         prev.y = __shfl_up_sync(0xffffffffu, y[R - 1].y, 1);
         float ph[R];
-        ph[0] = fm_phase(y[0], prev);   // lane 0's value is meaningless here: patched by k_fm_front_fixup
+        ph[0] = fm_phase(y[0], prev);   // lane 0's value is meaningless here: patched by the boundary pass at the end of the kernel
 #pragma unroll
         for (int r = 1; r < R; r++) ph[r] = fm_phase(y[r], y[r - 1]);
         float *os = out + m0;
@@ -213,25 +221,48 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_
 #pragma unroll
         for (int r = 0; r < R; r++) if (m0 + r == num - 1) *carry_out = y[r];
     }
-}
+    if (!DEMOD) return;
 
-// out[256 t] = phase(first[t] * conj(last[t-1])); sub-tile 0 uses the carried sample *carry
-__global__ void __launch_bounds__(256) k_fm_front_fixup(float *__restrict__ out, const float2 *__restrict__ bnd,
-                                                        const float2 *__restrict__ carry, long long n_sub, int sub_out) {
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_sub; t += (long long)gridDim.x * blockDim.x) {
-        const float2 prev = (t == 0) ? *carry : bnd[2 * (t - 1) + 1];
-        out[t * sub_out] = fm_phase(bnd[2 * t], prev);
+    // ---- the first output of every sub-tile: phase(first[t] * conj(last[t-1])), sub-tile 0 from the carried sample --------
+    __shared__ unsigned int is_last;
+    __threadfence();     // this thread's boundary samples and outputs, device-wide, before the ticket below
+    __syncthreads();
+    for (int u = threadIdx.x; u < cnt; u += blockDim.x) {
+        const long long t = s0 + u;
+        if (u == 0 && t != 0) continue;   // needs the previous CTA's last output
+        const float2 prev = (t == 0) ? *carry_in : __ldcg(bnd + 2 * (t - 1) + 1);
+        out[t * C::SUB_OUT] = fm_phase(__ldcg(bnd + 2 * t), prev);
+    }
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (is_last) {       // every other CTA fenced its boundary samples before taking its ticket
+        __threadfence();
+        for (int b = 1 + (int)threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+            const long long t = b * q + (b < rem ? b : rem);   // first sub-tile of CTA b
+            out[t * C::SUB_OUT] = fm_phase(__ldcg(bnd + 2 * t), __ldcg(bnd + 2 * (t - 1) + 1));
+        }
+        if (threadIdx.x == 0) *ticket = 0;   // for the next launch (stream order)
     }
 }
 
 // One launch of the fused kernel for tap capacity TK (the record's taps zero-padded up to it), D = 8.
 template <int TK, int NW, bool SYM, bool DEMOD>
 static int launch_front_inst(Ctx *c, const float *d_taps, const uint8_t *d_in, long long n_samples, const uint8_t *d_in_b,
-                             long long a_samples, float *d_out, long long num, float2 *d_bnd, float2 *d_carry_out, long long n_sub) {
+                             long long a_samples, float *d_out, long long num, float2 *d_bnd, float2 *d_carry_out, long long n_sub,
+                             const float2 *d_carry_in, unsigned int *d_ticket) {
     typedef FmCfg<TK, 8, 8, NW> C;
     SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_fm_front_ring<TK, 8, 8, NW, SYM, DEMOD>), C::SMEM_BYTES));
     int grid = (int)(n_sub < c->sm_count ? n_sub : c->sm_count);
-    k_fm_front_ring<TK, 8, 8, NW, SYM, DEMOD><<<grid, 32 * NW, C::SMEM_BYTES, c->s()>>>(d_in, a_samples / 8, d_in_b, n_samples / 8, d_out, num, d_bnd, d_carry_out, d_taps, n_sub);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * NW); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = c->s();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("SDR_B200_NO_PDL") != nullptr;   // measurement knob
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    const long long a_chunks = a_samples / 8, n_chunks = n_samples / 8;
+    SDR_CUDA(cudaLaunchKernelEx(&cfg, k_fm_front_ring<TK, 8, 8, NW, SYM, DEMOD>, d_in, a_chunks, d_in_b, n_chunks, d_out, num, d_bnd,
+                                d_carry_out, d_taps, n_sub, d_carry_in, d_ticket));
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     return SDR_OK;
@@ -243,24 +274,26 @@ static int launch_front_inst(Ctx *c, const float *d_taps, const uint8_t *d_in, l
 template <bool DEMOD>
 static int launch_front_any(Ctx *c, int taps_stored, const float *d_taps, bool symmetric, const uint8_t *d_in, long long n_samples,
                             const uint8_t *d_in_b, long long a_samples, float *d_out, long long num, float2 *d_bnd, float2 *d_carry_out,
-                            long long n_sub, const char **label) {
+                            long long n_sub, const char **label, const float2 *d_carry_in = nullptr, unsigned int *d_ticket = nullptr) {
     if (taps_stored > 64) {
-        if (symmetric && taps_stored == 128) { *label = "<128,8,8,sym,16w>"; return launch_front_inst<128, 16, true, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub); }
+        if (symmetric && taps_stored == 128) { *label = "<128,8,8,sym,16w>"; return launch_front_inst<128, 16, true, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub, d_carry_in, d_ticket); }
         *label = "<128,8,8>";
-        return launch_front_inst<128, 8, false, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub);
+        return launch_front_inst<128, 8, false, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub, d_carry_in, d_ticket);
     }
-    if (taps_stored > 32) { *label = "<64,8,8,16w>"; return launch_front_inst<64, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub); }
+    if (taps_stored > 32) { *label = "<64,8,8,16w>"; return launch_front_inst<64, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub, d_carry_in, d_ticket); }
     *label = "<32,8,8,16w>";
-    return launch_front_inst<32, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub);
+    return launch_front_inst<32, 16, false, DEMOD>(c, d_taps, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub, d_carry_in, d_ticket);
 }
 
 // Fused convert + decimate + demod of outputs [0, num) of a byte stream holding n_samples IQ pairs.  d_carry: previous
-// stream sample (re, im) on the device, read by the fix-up; d_carry_out receives the last decimated complex output;
-// d_bnd: scratch of 2 complex per sub-tile (ceil(num / 256) sub-tiles).  *done = num when the shape has a tuned kernel.
-// T = the record's stored tap count (d_taps zero-padded to >= 128 floats).
+// stream sample (re, im) on the device; d_carry_out receives the last decimated complex output (a different word: the
+// kernel reads the one while it writes the other); d_bnd: scratch of 2 complex per sub-tile (ceil(num / 256) sub-tiles);
+// d_ticket: one zero-initialised word the launches of a stream share (the kernel leaves it zero).  *done = num when the
+// shape has a tuned kernel.  T = the record's stored tap count (d_taps zero-padded to >= 128 floats).
 int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, const uint8_t *d_in, long long a_samples,
                     const uint8_t *d_in_b, long long n_samples, float *d_out, long long num, float2 *d_bnd,
-                    long long bnd_capacity_subtiles, const float2 *d_carry, float2 *d_carry_out, long long *done, const char **name) {
+                    long long bnd_capacity_subtiles, const float2 *d_carry, float2 *d_carry_out, unsigned int *d_ticket,
+                    long long *done, const char **name) {
     *done = 0;
     *name = "unfused";
     if (T > 128 || D != 8 || num <= 0) return SDR_OK;
@@ -271,15 +304,11 @@ int launch_fm_front(Ctx *c, int T, int D, const float *d_taps, bool symmetric, c
     if (bnd_capacity_subtiles < n_sub) return set_error(SDR_EINVAL, "launch_fm_front: boundary scratch too small");
     SDR_TRY(c->bind());
     const char *label = "";
-    SDR_TRY(launch_front_any<true>(c, T, d_taps, symmetric, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub, &label));
+    SDR_TRY(launch_front_any<true>(c, T, d_taps, symmetric, d_in, n_samples, d_in_b, a_samples, d_out, num, d_bnd, d_carry_out, n_sub, &label,
+                                   d_carry, d_ticket));
     static thread_local char nm[64];
     snprintf(nm, sizeof(nm), "fm_front_ring%s", label);
     *name = nm;
-    long long fg = (n_sub + 255) / 256;
-    if (fg > 4LL * c->sm_count) fg = 4LL * c->sm_count;
-    k_fm_front_fixup<<<(int)fg, 256, 0, c->s()>>>(d_out, d_bnd, d_carry, n_sub, 256);
-    c->launches++;
-    SDR_CUDA(cudaGetLastError());
     *done = num;
     return SDR_OK;
 }

@@ -15,11 +15,21 @@
 // registers, increasing tap order), multiplies by `scale` with one rounding and stores.  Every rounding of the un-fused
 // chain is reproduced (r is rounded to binary32 when it is written to shared memory, as it is when the resampler stage
 // writes it to HBM), so the fused stage is bit-identical to the three stages one after the other.
+// Both tap sets travel as LAUNCH PARAMETERS (616 bytes, by value): with every index a compile-time constant each tap is a
+// constant-bank operand of its FFMA -- no tap registers, no tap loads per tile (the first version re-read 154 taps per
+// thread and tile into registers, 128 registers per thread, 2 CTAs per SM; the kernel is a chain of short dependent
+// phases -- stage, resample, filter -- and what hides their latency is other CTAs on the same SM).
 // Roofline: 4 B in + 1.2 B out per input sample and 9 + 19.2 FMA per input sample: FP32-pipe bound, but the whole
 // low-rate end is ~11 % of the chain's arithmetic.
 #include "ring_common.cuh"
 
+#include <cstdlib>
+
 namespace sdr {
+
+#ifndef LOWRATE_MIN_CTAS
+#define LOWRATE_MIN_CTAS 5
+#endif
 
 template <int L, int M, int T>
 struct LrPhase {
@@ -55,17 +65,22 @@ __device__ __forceinline__ float seg_load(const float *a, long long na, const fl
     return i < nb ? __ldg(b + i) : 0.0f;
 }
 
+template <int TR, int TF> struct LowTaps { float r[TR]; float f[TF]; };
+
 template <int L, int M, int TR, int TF>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, LOWRATE_MIN_CTAS)
 k_fm_lowrate(const float *__restrict__ xa, long long na, const float *__restrict__ xb, long long nb, long long x0_global,
-             long long n0, float *__restrict__ out, long long num, const float *__restrict__ taps_r,
-             const float *__restrict__ taps_f, float scale) {
+             long long n0, float *__restrict__ out, long long num, const __grid_constant__ LowTaps<TR, TF> K, float scale) {
     typedef LowCfg<L, M, TR, TF> C;
     typedef LrPhase<L, M, TR> P;
     extern __shared__ __align__(16) float sm[];
     float *xs = sm;                    // [XS]
     float *rs = sm + ((C::XS + 3) / 4) * 4;   // [NR]
     const int t = threadIdx.x;
+    // programmatic dependent launch (see k_dec_ring): the next launch may be scheduled while this grid drains; this one
+    // touches global memory only after everything before it in the stream has completed
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     for (long long tile = blockIdx.x; tile * C::NZ < num; tile += gridDim.x) {
         const long long n_tile = n0 + tile * C::NZ;            // first output z of the tile (global index)
@@ -90,9 +105,6 @@ k_fm_lowrate(const float *__restrict__ xa, long long na, const float *__restrict
         }
         __syncthreads();
         {   // phase 1: thread t -> cycles c0 + 2t, c0 + 2t + 1
-            float tap[TR];
-#pragma unroll
-            for (int k = 0; k < TR; k++) tap[k] = __ldg(taps_r + k);
             const float4 *w = reinterpret_cast<const float4 *>(xs + t * C::LANE_IN);
             float acc[C::CY * L];
 #pragma unroll
@@ -109,7 +121,7 @@ k_fm_lowrate(const float *__restrict__ xa, long long na, const float *__restrict
                         for (int j = 0; j < L; j++) {
                             const int l = 4 * c4 + i - cy * M - P::i0(j);
                             if (l >= 0 && l < P::len(j))
-                                acc[cy * L + j] = fmaf(tap[(l >= 0 && l < P::len(j)) ? P::f(j) + l * L : 0], e[i], acc[cy * L + j]);
+                                acc[cy * L + j] = fmaf(K.r[(l >= 0 && l < P::len(j)) ? P::f(j) + l * L : 0], e[i], acc[cy * L + j]);
                         }
                     }
                 }
@@ -123,9 +135,6 @@ k_fm_lowrate(const float *__restrict__ xa, long long na, const float *__restrict
         }
         __syncthreads();
         {   // phase 2: 4 consecutive outputs per thread and pass
-            float cf[TF];
-#pragma unroll
-            for (int k = 0; k < TF; k++) cf[k] = __ldg(taps_f + k);
             const long long left = num - tile * C::NZ;
             const int nz = (int)(left < C::NZ ? left : C::NZ);
             for (int g = t; 4 * g < nz; g += C::NT) {
@@ -140,7 +149,7 @@ k_fm_lowrate(const float *__restrict__ xa, long long na, const float *__restrict
 #pragma unroll
                         for (int r = 0; r < 4; r++) {
                             const int k = 4 * c4 + i - r;
-                            if (k >= 0 && k < TF) acc[r] = fmaf(cf[(k >= 0 && k < TF) ? k : 0], e[i], acc[r]);
+                            if (k >= 0 && k < TF) acc[r] = fmaf(K.f[(k >= 0 && k < TF) ? k : 0], e[i], acc[r]);
                         }
                     }
                 }
@@ -158,7 +167,7 @@ k_fm_lowrate(const float *__restrict__ xa, long long na, const float *__restrict
 }
 
 template <int L, int M, int TR, int TF>
-static int launch_low(Ctx *c, const float *d_taps_r, const float *d_taps_f, float scale, Seg2 seg, long long n0, float *d_out,
+static int launch_low(Ctx *c, const float *h_taps_r, const float *h_taps_f, float scale, Seg2 seg, long long n0, float *d_out,
                       long long num) {
     typedef LowCfg<L, M, TR, TF> C;
     SDR_TRY(c->bind());
@@ -167,25 +176,35 @@ static int launch_low(Ctx *c, const float *d_taps_r, const float *d_taps_f, floa
     long long cap = 2LL * c->sm_count * 16;
     int grid = (int)(tiles < cap ? tiles : cap);
     const long long x0_global = (n0 * M + L - 1) / L;
-    k_fm_lowrate<L, M, TR, TF><<<grid, 256, C::SMEM_BYTES, c->s()>>>((const float *)seg.a, seg.na, (const float *)seg.b, seg.nb, x0_global,
-                                                                       n0, d_out, num, d_taps_r, d_taps_f, scale);
+    LowTaps<TR, TF> K;
+    for (int k = 0; k < TR; k++) K.r[k] = h_taps_r[k];
+    for (int k = 0; k < TF; k++) K.f[k] = h_taps_f[k];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = c->s();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("SDR_B200_NO_PDL") != nullptr;   // measurement knob
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    SDR_CUDA(cudaLaunchKernelEx(&cfg, k_fm_lowrate<L, M, TR, TF>, (const float *)seg.a, seg.na, (const float *)seg.b, seg.nb, x0_global,
+                                n0, d_out, num, K, scale));
     c->launches++;
     SDR_CUDA(cudaGetLastError());
     return SDR_OK;
 }
 
-int launch_fm_lowrate(Ctx *c, int L, int M, int n_taps_r, const float *d_taps_r, int n_taps_f, const float *d_taps_f, float scale,
+int launch_fm_lowrate(Ctx *c, int L, int M, int n_taps_r, const float *h_taps_r, int n_taps_f, const float *h_taps_f, float scale,
                       Seg2 seg, long long n0, float *d_out, long long num, long long *done, const char **name) {
     *done = 0;
     *name = "unfused";
     if (num <= 0) return SDR_OK;
     if (L == 3 && M == 10 && n_taps_f == 64 && n_taps_r == 90) {
         *name = "fm_lowrate<3,10,90,64>";
-        SDR_TRY((launch_low<3, 10, 90, 64>(c, d_taps_r, d_taps_f, scale, seg, n0, d_out, num)));
+        SDR_TRY((launch_low<3, 10, 90, 64>(c, h_taps_r, h_taps_f, scale, seg, n0, d_out, num)));
         *done = num;
     } else if (L == 3 && M == 10 && n_taps_f == 64 && n_taps_r == 31) {   // the FM example's own sets (examples/fm/Coeffs.hs)
         *name = "fm_lowrate<3,10,31,64>";
-        SDR_TRY((launch_low<3, 10, 31, 64>(c, d_taps_r, d_taps_f, scale, seg, n0, d_out, num)));
+        SDR_TRY((launch_low<3, 10, 31, 64>(c, h_taps_r, h_taps_f, scale, seg, n0, d_out, num)));
         *done = num;
     }
     return SDR_OK;

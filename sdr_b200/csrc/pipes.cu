@@ -412,14 +412,15 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     float *out = (float *)(p->fifo.p + p->fifo.wr);
     p->bnd.rd = p->bnd.wr = 0;
     SDR_TRY(p->bnd.reserve((size_t)(count / 256 + 2) * 16));
-    // the carried sample is double buffered: the fix-up reads the old one while the kernel writes the new one
+    // the carried sample is double buffered: the kernel's boundary pass reads the old one, its main loop writes the new one;
+    // the word behind the two samples is the kernel's ticket counter
     float *carry_in = p->d_last + 2 * p->last_sel, *carry_out = p->d_last + 2 * (p->last_sel ^ 1);
     long long done = 0;
     const char *name = nullptr;
     Seg2 seg = input_seg(p);   // element = byte
     SDR_TRY(launch_fm_front(p->ctx, f.T, f.D, f.d_taps, f.symmetric, (const uint8_t *)seg.a, seg.nb ? seg.na / 2 : have, (const uint8_t *)seg.b,
                             have, out, count, (float2 *)p->bnd.p, (long long)(p->bnd.cap / 16), (const float2 *)carry_in, (float2 *)carry_out,
-                            &done, &name));
+                            (unsigned int *)(p->d_last + 4), &done, &name));
     p->last_kernel = name;
     if (done < count) {
         SDR_TRY(materialize_ext(p));   // the un-fused stages read one contiguous segment
@@ -497,7 +498,7 @@ static int process_fm_low(sdr_pipe *p, long long fifo_have, long long batch) {
     Seg2 seg = seg_advance(input_seg(p), i_k - p->pos, 4);
     long long done = 0;
     const char *name = nullptr;
-    SDR_TRY(launch_fm_lowrate(p->ctx, r.L, r.M, r.n_taps, r.d_plain, f.T, f.d_taps, p->scale_k, seg, p->k_next, out, count, &done, &name));
+    SDR_TRY(launch_fm_lowrate(p->ctx, r.L, r.M, r.n_taps, r.h_plain.data(), f.T, f.h_taps.data(), p->scale_k, seg, p->k_next, out, count, &done, &name));
     p->last_kernel = name;
     if (done < count) {   // no fused kernel for the shape: the three stages one after the other through scratch
         const long long nr = count + f.T - 1;
@@ -742,8 +743,8 @@ int sdr_pipe_fm_frontend(sdr_decimator_t *d, int block_size_out, sdr_pipe_t **ou
     SDR_TRY(new_pipe(d->r.ctx, P_FMFRONT, out, &p));
     p->fir = &d->r; p->in_eb = 1; p->out_eb = 4; p->block_out = block_size_out; p->assert_name = "decimate";
     p->bnd.c = p->scratch_x.c = p->scratch_y.c = p->ctx;
-    SDR_CUDA(cudaMalloc(&p->d_last, 16));
-    SDR_CUDA(cudaMemsetAsync(p->d_last, 0, 16, p->ctx->stream));
+    SDR_CUDA(cudaMalloc(&p->d_last, 32));   // two carried samples (double buffer) + the fused kernel's ticket word
+    SDR_CUDA(cudaMemsetAsync(p->d_last, 0, 32, p->ctx->stream));
     return SDR_OK;
 }
 int sdr_pipe_fm_lowrate(sdr_resampler_t *r, int block_size_resampler, sdr_filter_t *f, int block_size_out, float scale, sdr_pipe_t **out) {

@@ -57,6 +57,7 @@ int FirRec::create(Ctx *c, bool is_complex, int factor, const float *coeffs, int
     symmetric = true;
     for (int k = 0; k < T / 2; k++) if (memcmp(&full[k], &full[T - 1 - k], sizeof(float)) != 0) { symmetric = false; break; }
     // the tuned kernels are instantiated for 32 / 64 / 128 taps and read their whole capacity: zero-padded on the device
+    h_taps.assign(full.begin(), full.begin() + T);
     const int t_alloc = round_up(T, 128) + 128;
     full.resize(t_alloc, 0.0f);
     SDR_CUDA(cudaMalloc(&d_taps, sizeof(float) * t_alloc));
@@ -193,6 +194,7 @@ int ResRec::create(Ctx *c, bool is_complex, int interpolation, int decimation, c
     }
     SDR_CUDA(cudaMalloc(&d_table, sizeof(float) * table.size()));
     SDR_CUDA(cudaMalloc(&d_prefix, sizeof(int) * ng));
+    h_plain.assign(coeffs, coeffs + n);
     SDR_CUDA(cudaMalloc(&d_plain, sizeof(float) * n));
     SDR_CUDA(cudaMemcpyAsync(d_plain, coeffs, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
     SDR_CUDA(cudaMemcpyAsync(d_table, table.data(), sizeof(float) * table.size(), cudaMemcpyHostToDevice, c->stream));

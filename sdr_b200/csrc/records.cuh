@@ -15,6 +15,7 @@ struct FirRec {
     int   T = 0;            // numCoeffsF / numCoeffsD: stored (possibly zero-padded) tap count
     int   arith = SDR_ARITH_FAST;
     float *d_taps = nullptr;       // T floats, full (symmetric halves expanded), zero padded
+    std::vector<float> h_taps;     // the same T floats on the host (kernels that take their taps as launch parameters)
     // EXACT arithmetic: the variant the reference's fast* constructor would pick on an AVX host, with the taps in the
     // layout that C function receives
     int   ex_W = 8, ex_layout = 0, ex_sym = 0, ex_T = 0;
@@ -44,6 +45,7 @@ struct ResRec {
     float *d_table = nullptr;  // [ng][row_stride]
     int   *d_prefix = nullptr; // [ng]
     float *d_plain = nullptr;  // the n_taps plain coefficients (tuned kernels index them as c[f + l L])
+    std::vector<float> h_plain; // the same on the host
     const char *last_kernel = "none";
     int create(Ctx *c, bool is_complex, int interpolation, int decimation, const float *coeffs, int n, int size_multiple);
     void destroy();
