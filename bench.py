@@ -816,38 +816,48 @@ def run_configs(args, ctx, dec, sdr_b200, L, peak):
         "k_dc_spec_tiles + k_dc_repair" if par else "k_dc_blocker")
     d_fin.free()
     # cfg4: the whole FM chain, u8 IQ in -> audio out, 32 MiB pushes (16 Mi IQ pairs each) of device-resident vectors read in
-    # place (SDR_DEVICE_HELD): two fused stages = front end (+ its 1-in-256 fix-up) and low-rate end per push
+    # place (SDR_DEVICE_HELD): two fused stages = front end and low-rate end.  The stream is 1 GiB (32 pushes) per pass so
+    # that the first launch's latency and the closing synchronisation of sdr_pipe_run weigh what they weigh in a running
+    # receiver; `x` is reused as the byte buffer.
     fil = sdr_b200.cudaFilterSymR(half, ctx=ctx)
     n_out = C.c_longlong()
     push = 1 << 25
+    cbytes = 8 * n
+    nc = cbytes // 2                                # IQ pairs per pass
+    ctx.synth_bytes(x, cbytes)
 
-    def time_chain(stages, label, key):
+    def time_chain(stages, label, key, thresholds=None):
         for a, b in zip(stages, stages[1:]):
             a.connect(b)
-        for p in stages:
+        for i, p in enumerate(stages):
             try:
-                L.check(L.lib.sdr_pipe_set_batch(p.h, 1 << 21))
+                L.check(L.lib.sdr_pipe_set_batch(p.h, thresholds[i] if thresholds else 1 << 21))
             except sdr_b200.SdrError:
                 pass
 
         def chain():
-            L.check(L.lib.sdr_pipe_run(stages[0].h, stages[-1].h, bbuf.ptr, push, nbytes // push, L.SDR_DEVICE_HELD, y.ptr, 2 * n, L.SDR_DEVICE,
+            L.check(L.lib.sdr_pipe_run(stages[0].h, stages[-1].h, x.ptr, push, cbytes // push, L.SDR_DEVICE_HELD, y.ptr, 2 * n, L.SDR_DEVICE,
                                        C.byref(n_out)))
         for _ in range(2):
             chain()
         ctx.sync()
         l0 = ctx.launches
         ms = timed(chain, steps=4, warm=0)
-        put(key, label, ms, n, 2.15, 32 + 9 / 8 + 64 * 3 / 80, " + ".join(
+        put(key, label, ms, nc, 2.15, 32 + 9 / 8 + 64 * 3 / 80, " + ".join(
             k for k in (L.lib.sdr_pipe_last_kernel(st.h).decode() for st in stages) if k != "none"))
-        out[key]["launches_per_push"] = (ctx.launches - l0) / 4 / (nbytes // push)
+        out[key]["launches_per_push"] = (ctx.launches - l0) / 4 / (cbytes // push)
+        out[key]["pushes_per_pass"] = cbytes // push
         out[key]["audio_samples_out"] = int(n_out.value)
         for p in stages:
             p.close()
 
     time_chain([sdr_b200.pipeFmFrontEnd(dec, BUF), sdr_b200.pipeFmLowRate(r, BUF, fil, BUF, 0.2)],
                "full FM pipe: u8 IQ -> [convert + decimate-by-8 (128 taps) + fmDemod] -> [resample 3/10 (90 taps) + 64-tap filter + x0.2], two fused "
-               "stages, 32 MiB device pushes read in place; per input IQ sample", "cfg4_chain")
+               "stages, 32 MiB device pushes read in place, the front end launches at every push; per input IQ sample", "cfg4_chain")
+    time_chain([sdr_b200.pipeFmFrontEnd(dec, BUF), sdr_b200.pipeFmLowRate(r, BUF, fil, BUF, 0.2)],
+               "the same two stages and 32 MiB pushes with launch thresholds sized for throughput (sdr_pipe_set_batch: front end every 4 pushes, "
+               "low-rate end every ~7): what a receiver that can afford 30 ms of latency would set", "cfg4_chain_batched",
+               thresholds=[1 << 23, 1 << 22])
     time_chain([sdr_b200.pipeFmFrontEnd(dec, BUF), sdr_b200.pipeFirResampler(r, BUF), sdr_b200.pipeFirFilter(fil, BUF), sdr_b200.pipeScale(0.2, ctx)],
                "the same chain with the low-rate end as three separate stages (round 1's form)", "cfg4_chain_unfused_lowrate")
     # the fused front end alone (u8 IQ -> phase)

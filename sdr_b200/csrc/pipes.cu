@@ -213,6 +213,15 @@ static int materialize_ext(sdr_pipe *p) {
     p->ext_p = nullptr; p->ext_bytes = 0;
     return SDR_OK;
 }
+// After a launch of a fused byte-fed stage: the few samples it left over.  When they lie in the in-place run and the next
+// launch can read them there (16-byte aligned start, nothing carried in the stage's own buffer) they STAY in the caller's
+// vector -- his until sdr_pipe_sync -- and the next adjacent push simply extends the run: no copy between two launches, so
+// consecutive kernels are neighbours in the stream and overlap their launch latency (programmatic dependent launch).
+// Otherwise (and always for a connected upstream stage's FIFO region, see sdr_pipe_push) the tail moves into the stage.
+static int park_tail(sdr_pipe *p) {
+    if (p->ext_bytes && p->in.size() == 0 && (((uintptr_t)p->ext_p) & 15) == 0) return SDR_OK;
+    return materialize_ext(p);
+}
 // drop `bytes` from the front of the resident stream (tail first, then the in-place run)
 static void consume_input(sdr_pipe *p, size_t bytes) {
     const size_t live = p->in.size();
@@ -435,7 +444,7 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
         p->skip += 2 * (count * f.D - adv);
         consume_input(p, (size_t)adv * 2);
     }
-    SDR_TRY(materialize_ext(p));   // the short tail moves behind the stage's own buffer; the caller's vectors are released
+    SDR_TRY(park_tail(p));
     if (p->in.size() <= (1u << 16) && p->in.rd > p->in.cap / 4) SDR_TRY(p->in.realign(0));
     return SDR_OK;
 }
@@ -473,7 +482,7 @@ static int process_u8_decim(sdr_pipe *p, long long fifo_have, long long batch) {
         p->skip += 2 * (count * f.D - adv);
         consume_input(p, (size_t)adv * 2);
     }
-    SDR_TRY(materialize_ext(p));
+    SDR_TRY(park_tail(p));
     if (p->in.size() <= (1u << 16) && p->in.rd > p->in.cap / 4) SDR_TRY(p->in.realign(0));
     return SDR_OK;
 }
