@@ -29,6 +29,16 @@
 
 namespace sdr {
 
+// tools/fm_timeline.cu compiles this file with SDR_FM_TIMING to get a per-warp time line of one launch (measurement aid;
+// the library is built without it)
+#ifdef SDR_FM_TIMING
+__device__ unsigned long long g_fm_timing[160 * 16 * 8];
+#define FM_T(i) do { if ((threadIdx.x & 31) == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+                     g_fm_timing[(blockIdx.x * 16 + (threadIdx.x >> 5)) * 8 + (i)] = t_; } } while (0)
+#else
+#define FM_T(i) do { } while (0)
+#endif
+
 template <int T, int D, int R, int NW>
 struct FmCfg {
     static_assert(T % D == 0 && D == 8 && R == 8, "one decimation block = 8 IQ pairs = one 16-byte chunk");
@@ -92,6 +102,7 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_
     long long s0 = blockIdx.x * q + (blockIdx.x < rem ? blockIdx.x : rem);
     int cnt = (int)(q + (blockIdx.x < rem ? 1 : 0));   // >= 1: the grid never exceeds the number of sub-tiles
 
+    FM_T(0);
     // programmatic dependent launch, as in k_dec_ring: the next launch in the stream may be scheduled while this one drains
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t ring = smem_u32(smem);
@@ -109,11 +120,25 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_
     auto chunk_src = [&](long long g) -> const unsigned char * {
         return g < a_chunks ? in + g * 16 : in_b + (g - a_chunks) * 16;
     };
+    const uint32_t lane_dst = (uint32_t)((lane >> 3) * C::SEG_STRIDE + (lane & 7) * 16);   // chunk `lane` of a group of 32
     auto issue_fill = [&](int u) {
         const int slot = u % C::NS;
         const int nchunk = (u == cnt) ? C::HALO_SEGS * R : 32 * R;   // halo-only fill: the first segments
         const long long chunk0 = (s0 + u) * (long long)(32 * R);
         const uint32_t dst = ring + slot * C::SLOT_BYTES;
+        // fast path (all fills but the one or two at a segment boundary / the end of the stream, and the halo-only one):
+        // the whole sub-tile lies inside one source -- eight copies at constant offsets from two lane registers
+        const bool in_a = chunk0 + 32 * R <= a_chunks, in_b_ = chunk0 >= a_chunks && chunk0 + 32 * R <= n_chunks;
+        if (nchunk == 32 * R && (in_a || in_b_)) {
+            const unsigned char *src = (in_a ? in + chunk0 * 16 : in_b + (chunk0 - a_chunks) * 16) + lane * 16;
+#pragma unroll
+            for (int i = 0; i < R; i++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + lane_dst + i * 4 * C::SEG_STRIDE), "l"(src + i * 512) : "memory");
+            if (slot == 0 && lane < C::HALO_SEGS * R)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + C::NS * C::SLOT_BYTES + lane_dst), "l"(src) : "memory");
+            cp_async_arrive(bar_full + 8 * slot);
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < R; i++) {
             const int c = i * 32 + lane;
@@ -136,14 +161,24 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_
     for (int k = 0; k < NT; k++) tap[k] = __ldg(taps + k);   // written once when the record was made: safe before the wait
     // everything before us in the stream has completed and flushed from here on (no-op without an early trigger)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    FM_T(1);
 
-    for (int u = warp; u < C::NS && u <= cnt; u += C::NWARPS) issue_fill(u);
+    // One fill per warp up front; the second generation of slots (u + NW) is requested from inside the first iteration,
+    // once the first data has landed: asked for at once, the whole 148 KB ring queues behind the memory system and every
+    // warp sits in its second fill for 2 us before it computes anything (tools/fm_timeline.cu).
+    static_assert(C::NS == 2 * C::NWARPS || C::NS == 3 * C::NWARPS, "slots per warp");
+    if (warp <= cnt) issue_fill(warp);
+    FM_T(2);
     const u64 k_scale = dup2(0.0078125f), k_bias = dup2(-65537.0f);
 
     for (int u = warp; u < cnt; u += C::NWARPS) {
         const int slot = u % C::NS, slot2 = (u + 1) % C::NS;
         mbar_wait(bar_full + 8 * slot, (u / C::NS) & 1);
         mbar_wait(bar_full + 8 * slot2, ((u + 1) / C::NS) & 1);
+        if (u == warp) {   // first iteration: the rest of this warp's slots (never used before: no empty-wait)
+            FM_T(3);
+            for (int v = u + C::NWARPS; v < C::NS && v <= cnt; v += C::NWARPS) issue_fill(v);
+        }
 
         const unsigned char *base = smem + slot * C::SLOT_BYTES + lane * C::SEG_STRIDE;
         u64 acc[R];
@@ -221,6 +256,7 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_
 #pragma unroll
         for (int r = 0; r < R; r++) if (m0 + r == num - 1) *carry_out = y[r];
     }
+    FM_T(4);
     if (!DEMOD) return;
 
     // ---- the first output of every sub-tile: phase(first[t] * conj(last[t-1])), sub-tile 0 from the carried sample --------
@@ -243,6 +279,7 @@ k_fm_front_ring(const uint8_t *__restrict__ in, long long a_chunks, const uint8_
         }
         if (threadIdx.x == 0) *ticket = 0;   // for the next launch (stream order)
     }
+    FM_T(5);
 }
 
 // One launch of the fused kernel for tap capacity TK (the record's taps zero-padded up to it), D = 8.
