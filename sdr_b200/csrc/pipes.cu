@@ -147,6 +147,7 @@ struct sdr_pipe {
     const char *last_kernel = "none";
     sdr_pipe *downstream = nullptr;
     sdr_pipe *upstream = nullptr;     // the stage connected in front of this one (unlinked when either side is destroyed)
+    bool ext_fwd = false;             // the in-place run lies in the upstream stage's FIFO (held there, see fifo_reserve)
     long long skip = 0;               // input elements still to drop: a decimation factor larger than the tap count skips
                                       // past the resident data (the reference's VG.drop (count*D - len), Filter.hs:610)
     const char *assert_name = "";
@@ -210,8 +211,24 @@ static int materialize_ext(sdr_pipe *p) {
     SDR_TRY(p->in.reserve(p->ext_bytes));
     SDR_CUDA(cudaMemcpyAsync(p->in.p + p->in.wr, p->ext_p, p->ext_bytes, cudaMemcpyDeviceToDevice, p->ctx->stream));
     p->in.wr += p->ext_bytes;
-    p->ext_p = nullptr; p->ext_bytes = 0;
+    p->ext_p = nullptr; p->ext_bytes = 0; p->ext_fwd = false;
     return SDR_OK;
+}
+// A connected stage whose launch threshold (sdr_pipe_set_batch) has not been reached keeps the vectors its upstream stage
+// handed over WHERE THEY ARE, in that stage's FIFO (round 1 copied every hand-over into the stage: 8 MB per 32 MiB push of
+// the FM chain, a quarter of the front-end kernel's time).  The upstream stage then neither rewinds nor moves its FIFO: it
+// appends behind the region, so the next hand-over is adjacent and extends the run, until it runs out of room -- only then
+// does the downstream stage take what it still references into its own buffer.
+static bool fifo_leased(const sdr_pipe *p) { return p->downstream && p->downstream->ext_fwd && p->downstream->ext_bytes > 0; }
+static int fifo_reserve(sdr_pipe *p, size_t bytes) {
+    if (fifo_leased(p) && p->fifo.wr + bytes > p->fifo.cap) SDR_TRY(materialize_ext(p->downstream));
+    if (!fifo_leased(p) && p->fifo.rd == p->fifo.wr && !p->fifo.fixed) p->fifo.rd = p->fifo.wr = 0;
+    return p->fifo.reserve(bytes);
+}
+// `bytes` at the front of the FIFO have been handed to the downstream stage
+static void fifo_forwarded(sdr_pipe *p, size_t bytes) {
+    if (fifo_leased(p)) p->fifo.rd += bytes;   // no rewind: the region is still being referenced
+    else p->fifo.consume(bytes);
 }
 // After a launch of a fused byte-fed stage: the few samples it left over.  When they lie in the in-place run and the next
 // launch can read them there (16-byte aligned start, nothing carried in the stage's own buffer) they STAY in the caller's
@@ -219,7 +236,7 @@ static int materialize_ext(sdr_pipe *p) {
 // consecutive kernels are neighbours in the stream and overlap their launch latency (programmatic dependent launch).
 // Otherwise (and always for a connected upstream stage's FIFO region, see sdr_pipe_push) the tail moves into the stage.
 static int park_tail(sdr_pipe *p) {
-    if (p->ext_bytes && p->in.size() == 0 && (((uintptr_t)p->ext_p) & 15) == 0) return SDR_OK;
+    if (p->ext_bytes && !p->ext_fwd && p->in.size() == 0 && (((uintptr_t)p->ext_p) & 15) == 0) return SDR_OK;
     return materialize_ext(p);
 }
 // drop `bytes` from the front of the resident stream (tail first, then the in-place run)
@@ -295,7 +312,7 @@ static int persist_try(sdr_pipe *p, bool *taken) {
             const long long na = (long long)(p->in.size() / p->in_eb), nb = (long long)(p->ext_bytes / p->in_eb);
             const long long m1 = (na + f.D - 1) / f.D;
             if (m1 * f.D - na + f.T > nb) return SDR_OK;                      // not enough of the run yet
-            SDR_TRY(p->fifo.reserve((size_t)m1 * p->out_eb));
+            SDR_TRY(fifo_reserve(p, (size_t)m1 * p->out_eb));
             SDR_TRY(launch_fir_generic(p->ctx, f.cplx, f.T, f.D, f.d_taps, input_seg(p), p->fifo.p + p->fifo.wr, m1));
             p->fifo.wr += (size_t)m1 * p->out_eb;
             consume_input(p, (size_t)(m1 * f.D) * p->in_eb);
@@ -309,7 +326,7 @@ static int persist_try(sdr_pipe *p, bool *taken) {
         if (!dec_persist_geometry(f.T, f.D, f.cplx, &S.run_samples, &S.halo_samples)) return SDR_OK;
         const long long max_samples = p->persist_max;
         const long long out_bytes = (max_samples / f.D + 1) * (long long)p->out_eb;
-        SDR_TRY(p->fifo.reserve((size_t)out_bytes));
+        SDR_TRY(fifo_reserve(p, (size_t)out_bytes));
         const long long runs_total = max_samples / S.run_samples;
         const size_t need = sizeof(PersistHdr) + (size_t)(runs_total + 1) * 4;
         if (need > S.ctl_bytes) {
@@ -355,7 +372,7 @@ static int forward(sdr_pipe *p) {
         if (nb > 0 && is_fir_kind(p->downstream->kind)) {
             // a FIR stage only sees the flat stream: hand it all complete vectors as one contiguous push
             SDR_TRY(pipe_push_any(p->downstream, p->fifo.p + p->fifo.rd, nb * p->block_out, MEM_FWD));
-            p->fifo.consume((size_t)(nb * p->block_out) * p->out_eb);
+            fifo_forwarded(p, (size_t)(nb * p->block_out) * p->out_eb);
         } else if (nb > 0) {
             // element-wise stages yield one vector per awaited vector: one launch over all of them, but the vector
             // structure (nb vectors of block_out elements) is kept in the stage's queue
@@ -373,7 +390,7 @@ static int forward(sdr_pipe *p) {
             if (shortest >= need) {
                 p->vec_lens.clear();
                 SDR_TRY(pipe_push_any(d, p->fifo.p + p->fifo.rd, total, MEM_FWD));
-                p->fifo.consume((size_t)total * p->out_eb);
+                fifo_forwarded(p, (size_t)total * p->out_eb);
                 return SDR_OK;
             }
         }
@@ -381,7 +398,7 @@ static int forward(sdr_pipe *p) {
             long long n = p->vec_lens.front();
             p->vec_lens.pop_front();
             SDR_TRY(pipe_push_any(p->downstream, p->fifo.p + p->fifo.rd, n, is_fir_kind(p->downstream->kind) ? (int)MEM_FWD : (int)SDR_DEVICE));
-            p->fifo.consume((size_t)n * p->out_eb);
+            fifo_forwarded(p, (size_t)n * p->out_eb);
         }
     }
     return SDR_OK;
@@ -417,7 +434,7 @@ static int process_fm_front(sdr_pipe *p, long long fifo_have, long long batch) {
     SDR_TRY(flush_pending(p));
     TraceScope tr("fm_front", p->ctx, count);
     SDR_TRY(fifo_writable(p));
-    SDR_TRY(p->fifo.reserve((size_t)count * 4));
+    SDR_TRY(fifo_reserve(p, (size_t)count * 4));
     float *out = (float *)(p->fifo.p + p->fifo.wr);
     p->bnd.rd = p->bnd.wr = 0;
     SDR_TRY(p->bnd.reserve((size_t)(count / 256 + 2) * 16));
@@ -459,7 +476,7 @@ static int process_u8_decim(sdr_pipe *p, long long fifo_have, long long batch) {
     SDR_TRY(flush_pending(p));
     TraceScope tr("u8_decimator", p->ctx, count);
     SDR_TRY(fifo_writable(p));
-    SDR_TRY(p->fifo.reserve((size_t)count * 8));
+    SDR_TRY(fifo_reserve(p, (size_t)count * 8));
     float *out = (float *)(p->fifo.p + p->fifo.wr);
     long long done = 0;
     const char *name = nullptr;
@@ -501,7 +518,7 @@ static int process_fm_low(sdr_pipe *p, long long fifo_have, long long batch) {
     SDR_TRY(flush_pending(p));
     TraceScope tr("fm_lowrate", p->ctx, count);
     SDR_TRY(fifo_writable(p));
-    SDR_TRY(p->fifo.reserve((size_t)count * 4));
+    SDR_TRY(fifo_reserve(p, (size_t)count * 4));
     float *out = (float *)(p->fifo.p + p->fifo.wr);
     const long long i_k = (p->k_next * r.M + r.L - 1) / r.L;   // first sample of resampler output k_next
     Seg2 seg = seg_advance(input_seg(p), i_k - p->pos, 4);
@@ -546,7 +563,7 @@ static int process_fir(sdr_pipe *p, bool force = false) {
             TraceScope tr("resampler", p->ctx, count);
             long long i_k = (p->k_next * r.M + r.L - 1) / r.L;   // ceil(k M / L): first sample of output k
             SDR_TRY(fifo_writable(p));
-            SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
+            SDR_TRY(fifo_reserve(p, (size_t)count * p->out_eb));
             SDR_TRY(r.run(input_seg(p), i_k - p->pos, (int)(p->k_next % r.ng), p->fifo.p + p->fifo.wr, count, false));
             p->fifo.wr += (size_t)count * p->out_eb;
             p->k_next = total_out;
@@ -584,7 +601,7 @@ static int process_fir(sdr_pipe *p, bool force = false) {
         SDR_TRY(flush_pending(p));
         TraceScope tr(p->kind == P_FILTER ? "filter" : "decimator", p->ctx, count);
         SDR_TRY(fifo_writable(p));
-        SDR_TRY(p->fifo.reserve((size_t)count * p->out_eb));
+        SDR_TRY(fifo_reserve(p, (size_t)count * p->out_eb));
         SDR_TRY(f.run(input_seg(p), 0, p->fifo.p + p->fifo.wr, count, false));
         p->fifo.wr += (size_t)count * p->out_eb;
         {
@@ -665,10 +682,10 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, lon
             // vector somewhere else first moves the run collected so far behind the stage's own buffer.
             SDR_TRY(flush_pending(p));
             const size_t bytes = (size_t)n * p->in_eb;
-            if (p->ext_bytes && p->ext_p + p->ext_bytes == (const char *)src) p->ext_bytes += bytes;
+            if (p->ext_bytes && p->ext_fwd == (mem == MEM_FWD) && p->ext_p + p->ext_bytes == (const char *)src) p->ext_bytes += bytes;
             else { SDR_TRY(materialize_ext(p)); p->ext_p = (const char *)src; p->ext_bytes = bytes; }
+            p->ext_fwd = (mem == MEM_FWD);   // what no launch consumes stays in the upstream stage's FIFO, held in place there
             SDR_TRY(process_fir(p));
-            if (mem == MEM_FWD) SDR_TRY(materialize_ext(p));   // the upstream stage is about to reuse its FIFO
             return forward(p);
         }
         SDR_TRY(materialize_ext(p));   // keeps the stream in order when held and copied pushes are mixed
@@ -694,7 +711,7 @@ static int pipe_push_any(sdr_pipe *p, const void *src, long long n, int mem, lon
         n_out = n / 2;   // complex samples out
     }
     SDR_TRY(fifo_writable(p));
-    SDR_TRY(p->fifo.reserve((size_t)n_out * p->out_eb));
+    SDR_TRY(fifo_reserve(p, (size_t)n_out * p->out_eb));
     void *d_dst = p->fifo.p + p->fifo.wr;
     if (p->kind == P_CONVERT) SDR_TRY(launch_convert_u8(p->ctx, (const uint8_t *)d_src, (float *)d_dst, n));
     else if (p->kind == P_SCALE) SDR_TRY(launch_scale(p->ctx, p->scale_k, (const float *)d_src, (float *)d_dst, n));
@@ -818,7 +835,9 @@ int sdr_pipe_destroy(sdr_pipe_t *p) {
     if (p->ps.ev) cudaEventDestroy(p->ps.ev);
     if (p->ps.ctl) cudaFreeHost(p->ps.ctl);
     if (p->ps.d_relay) cudaFree(p->ps.d_relay);
-    // unlink: a neighbour that outlives this stage must not forward into (or be unlinked from) freed memory
+    // unlink: a neighbour that outlives this stage must not forward into (or be unlinked from) freed memory, nor keep
+    // referring to vectors held in this stage's FIFO
+    if (fifo_leased(p)) { materialize_ext(p->downstream); cudaStreamSynchronize(p->ctx->stream); }
     if (p->upstream) p->upstream->downstream = nullptr;
     if (p->downstream) p->downstream->upstream = nullptr;
     p->in.release(); p->fifo.release(); p->bnd.release(); p->scratch_x.release(); p->scratch_y.release();
@@ -922,7 +941,7 @@ int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs) {
                              : is_byte_fed(p->kind) ? 2 * p->fir->D : p->fir->D;
         long long taps = is_resamp_kind(p->kind) ? p->res->T : p->fir->T;
         SDR_TRY(p->in.reserve((size_t)(2 * (min_outputs + p->block_out) * in_per_out + taps) * p->in_eb));
-        SDR_TRY(p->fifo.reserve((size_t)(2 * (min_outputs + p->block_out)) * p->out_eb));
+        SDR_TRY(fifo_reserve(p, (size_t)(2 * (min_outputs + p->block_out)) * p->out_eb));
     }
     return SDR_OK;
 }
@@ -1024,7 +1043,7 @@ int sdr_pipe_state_restore(sdr_pipe_t *p, const void *buf, size_t bytes) {
     }
     q += h.in_bytes;
     if (h.fifo_bytes) {
-        SDR_TRY(p->fifo.reserve((size_t)h.fifo_bytes));
+        SDR_TRY(fifo_reserve(p, (size_t)h.fifo_bytes));
         SDR_CUDA(cudaMemcpyAsync(p->fifo.p, q, (size_t)h.fifo_bytes, cudaMemcpyHostToDevice, st));
         p->fifo.wr = (size_t)h.fifo_bytes;
     }
@@ -1281,7 +1300,10 @@ int sdr_pipe_connect(sdr_pipe_t *src, sdr_pipe_t *dst) {
     }
     if (dst->upstream && dst->upstream != src)
         return set_error(SDR_EINVAL, "sdr_pipe_connect: the destination stage already has an upstream stage");
-    if (src->downstream) src->downstream->upstream = nullptr;
+    if (src->downstream && src->downstream != dst) {
+        if (fifo_leased(src)) { SDR_TRY(src->ctx->bind()); SDR_TRY(materialize_ext(src->downstream)); }
+        src->downstream->upstream = nullptr;
+    }
     src->downstream = dst;
     dst->upstream = src;
     return SDR_OK;

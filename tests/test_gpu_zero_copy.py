@@ -172,3 +172,41 @@ def test_fm_chain_two_fused_stages_equal_six_stages(sdr, ctx):
         assert np.array_equal(u.view(np.uint32), v.view(np.uint32))
     for p in [fe, lo] + q:
         p.close()
+
+
+@pytest.mark.parametrize("threshold,order", [(1 << 14, "down_first"), (1 << 18, "up_first"), (1 << 23, "down_first")])
+def test_connected_stage_keeps_handed_over_vectors_in_the_upstream_fifo(sdr, ctx, threshold, order):
+    """a launch threshold on the downstream stage (sdr_pipe_set_batch) makes hand-overs accumulate: they stay in the upstream
+    stage's FIFO (no copy), which must then neither rewind nor move under them -- until it runs out of room (with the 2^23
+    threshold nothing launches before the end of the input: the upstream FIFO has to grow several times under the run).
+    Same stream as the un-thresholded stages given everything at once; either stage may be destroyed first."""
+    from sdr_b200 import _lib as L
+    taps = synth.windowed_sinc_taps(128, 1 / 16)
+    t90 = synth.windowed_sinc_taps(90, 1 / 20, gain=3.0)
+    d = sdr.cudaDecimatorC(8, taps, sizeMultiple=4)
+    r = sdr.cudaResamplerR(3, 10, t90, sizeMultiple=8)
+    f = sdr.cudaFilterSymR(FM["coeffsAudioFilter"])
+    vec, nvec = 1 << 20, 15
+    raw = np.random.default_rng(11).integers(0, 256, vec * nvec, dtype=np.uint8)
+    ref = []
+    stages = [sdr.pipeFmFrontEnd(d, 8192), sdr.pipeFmLowRate(r, 8192, f, 8192, 0.2)]
+    stages[0].connect(stages[1])
+    stages[0].push(raw)
+    stages[1].sync()
+    _drain(stages[1], ref)
+    for p in stages:
+        p.close()
+    ref = np.concatenate(ref)
+    fe, lo = sdr.pipeFmFrontEnd(d, 8192), sdr.pipeFmLowRate(r, 8192, f, 8192, 0.2)
+    fe.connect(lo)
+    L.check(L.lib.sdr_pipe_set_batch(lo.h, threshold))
+    dbuf = ctx.to_device(raw)
+    out = ctx.alloc(4 * len(ref) + 65536)
+    n_out = C.c_longlong()
+    L.check(L.lib.sdr_pipe_run(fe.h, lo.h, dbuf.ptr, vec, nvec, L.SDR_DEVICE_HELD, out.ptr, len(ref) + 8192, L.SDR_DEVICE, C.byref(n_out)))
+    assert n_out.value == len(ref) and len(ref) > 100000
+    got = out.to_host(np.float32, len(ref))
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    for p in ((lo, fe) if order == "down_first" else (fe, lo)):
+        p.close()
+    dbuf.free(); out.free()

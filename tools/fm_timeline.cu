@@ -49,6 +49,15 @@ int main(int argc, char **argv) {
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         printf("rep %d status %d %s done %lld: %.1f us (events)\n", rep, st, name, done, ms * 1e3);
     }
+    for (int rep = 0; rep < 3; rep++) {   // cadence of back-to-back launches (programmatic dependent launch unless SDR_B200_NO_PDL)
+        cudaEventRecord(e0, c.stream);
+        for (int k = 0; k < 16; k++)
+            launch_fm_front(&c, 128, 8, d_taps, true, d_in, n, nullptr, n, d_out, num, d_bnd, n / 8 / 256 + 2, d_carry, d_carry + 1, d_ticket, &done, &name);
+        cudaEventRecord(e1, c.stream);
+        cudaStreamSynchronize(c.stream);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        printf("16 launches back to back: %.1f us each\n", ms * 1e3 / 16);
+    }
     std::vector<unsigned long long> t(160 * 16 * 8);
     cudaMemcpyFromSymbol(t.data(), g_fm_timing, t.size() * 8);
     unsigned long long t0 = ~0ULL;
