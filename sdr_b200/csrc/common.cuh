@@ -96,7 +96,7 @@ Ctx *default_ctx(int *status);   // per-thread context behind the reference-sign
 // outputs it produced (a multiple of its tile; 0: no tuned kernel for the shape) and the caller finishes the rest with
 // launch_fir_generic.  d_taps must be zero-padded to at least 128 floats (FirRec does that).
 int launch_dec_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_taps, Seg2 seg, void *d_out, long long num,
-                    long long *done, const char **name);
+                    long long *done, const char **name, const float *h_taps = nullptr);
 // persistent consumer (kernels_fast.cu): see PersistCtl there; ctl = page-locked mapped control block
 bool dec_persist_geometry(int taps_stored, int D, bool cplx, int *run_samples, int *halo_samples);
 int launch_dec_persist(Ctx *c, int taps_stored, int D, bool cplx, const float *d_taps, const void *d_in, void *d_out, void *ctl,

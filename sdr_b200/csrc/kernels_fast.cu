@@ -51,10 +51,14 @@ struct RingCfg {
     static_assert(CPLX ? R % 2 == 0 : R % 4 == 0, "outputs per lane are stored in 16-byte groups");
 };
 
-template <bool CPLX, int T, int D, int R>
+// TP: the taps travel as launch parameters (constant bank) instead of living in registers -- what makes 256 taps fit.
+template <int N> struct TapBlock { float t[N]; };
+
+template <bool CPLX, int T, int D, int R, bool TP = false>
 __global__ void __launch_bounds__(256, 1)
 k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restrict__ in_b, long long total_bytes,
-           void *__restrict__ out, long long num, const float *__restrict__ taps, long long n_sub) {
+           void *__restrict__ out, long long num, const float *__restrict__ taps, long long n_sub,
+           const __grid_constant__ TapBlock<TP ? T : 1> K) {
     typedef RingCfg<CPLX, T, D, R> C;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,9 +152,12 @@ k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restric
 
     for (int u = warp; u < C::NS && u <= cnt; u += C::NWARPS) issue_fill(u);
 
-    float tap[T];
+    float tap[TP ? 1 : T];
+    if (!TP) {
 #pragma unroll
-    for (int k = 0; k < T; k++) tap[k] = __ldg(taps + k);
+        for (int k = 0; k < (TP ? 1 : T); k++) tap[k] = __ldg(taps + k);
+    }
+#define SDR_TAP(k) (TP ? K.t[TP ? (k) : 0] : tap[TP ? 0 : (k)])
 
     for (int u = warp; u < cnt; u += C::NWARPS) {
         const int slot = u % C::NS, par = (u / C::NS) & 1;
@@ -171,8 +178,8 @@ k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restric
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const int k0 = e0 - r * D, k1 = e0 + 1 - r * D;
-                    if (k0 >= 0 && k0 < T) acc[r] = ffma2(v.x, dup2(tap[k0 < 0 ? 0 : (k0 >= T ? 0 : k0)]), acc[r]);
-                    if (k1 >= 0 && k1 < T) acc[r] = ffma2(v.y, dup2(tap[k1 < 0 ? 0 : (k1 >= T ? 0 : k1)]), acc[r]);
+                    if (k0 >= 0 && k0 < T) acc[r] = ffma2(v.x, dup2(SDR_TAP(k0 < 0 ? 0 : (k0 >= T ? 0 : k0))), acc[r]);
+                    if (k1 >= 0 && k1 < T) acc[r] = ffma2(v.y, dup2(SDR_TAP(k1 < 0 ? 0 : (k1 >= T ? 0 : k1))), acc[r]);
                 }
             }
             u64 *os = reinterpret_cast<u64 *>(out) + m0;
@@ -201,7 +208,7 @@ k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restric
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const int k = e0 + i - r * D;
-                        if (k >= 0 && k < T) acc[r] = fmaf(tap[k < 0 ? 0 : (k >= T ? 0 : k)], e[i], acc[r]);
+                        if (k >= 0 && k < T) acc[r] = fmaf(SDR_TAP(k < 0 ? 0 : (k >= T ? 0 : k)), e[i], acc[r]);
                     }
                 }
             }
@@ -232,8 +239,8 @@ k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restric
     }
 }
 
-template <bool CPLX, int T, int D, int R>
-static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long long num, long long *done) {
+template <bool CPLX, int T, int D, int R, bool TP = false>
+static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long long num, long long *done, const float *h_taps = nullptr) {
     typedef RingCfg<CPLX, T, D, R> C;
     constexpr int EB = C::EB, EPC = C::EPC;
     const long long n_in = seg.na + seg.nb;
@@ -264,7 +271,7 @@ static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long 
     }
     (void)needed2;
     SDR_TRY(c->bind());
-    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_ring<CPLX, T, D, R>), C::SMEM_BYTES));
+    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_ring<CPLX, T, D, R, TP>), C::SMEM_BYTES));
     int sms = c->sm_count - c->reserve_sms;
     if (sms < 1) sms = 1;
     int grid = (int)(n_sub < sms ? n_sub : sms);
@@ -278,7 +285,9 @@ static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long 
         static const bool no_pdl = getenv("SDR_B200_NO_PDL") != nullptr;   // measurement knob
         cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
         const void *a0 = seg.a, *b0 = seg.b;
-        SDR_CUDA(cudaLaunchKernelEx(&cfg, k_dec_ring<CPLX, T, D, R>, a0, a_bytes, b0, total_bytes, d_out, num_mask, d_taps, n_sub));
+        TapBlock<TP ? T : 1> K = {};
+        if (TP) for (int k = 0; k < T; k++) K.t[TP ? k : 0] = h_taps[k];
+        SDR_CUDA(cudaLaunchKernelEx(&cfg, k_dec_ring<CPLX, T, D, R, TP>, a0, a_bytes, b0, total_bytes, d_out, num_mask, d_taps, n_sub, K));
     }
     c->launches++;
     SDR_CUDA(cudaGetLastError());
@@ -288,7 +297,7 @@ static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long 
 // true when launch_dec_fast would produce ALL `num` outputs in one launch (no generic tail to fork): same conditions as
 // the covering mode of launch_ring
 bool dec_fast_will_cover(bool cplx, int taps_stored, int D, Seg2 seg, long long num) {
-    if (num <= 0 || taps_stored > 128 || (D != 4 && D != 8 && D != 16)) return false;
+    if (num <= 0 || taps_stored > 256 || (D != 4 && D != 8 && D != 16)) return false;
     const int epc = cplx ? 2 : 4;
     return (((uintptr_t)seg.a) & 15) == 0 && (seg.na % epc) == 0 && (seg.nb == 0 || (((uintptr_t)seg.b) & 15) == 0) &&
            ((seg.na + seg.nb) % epc) == 0;
@@ -296,12 +305,29 @@ bool dec_fast_will_cover(bool cplx, int taps_stored, int D, Seg2 seg, long long 
 
 // x = seg.a ++ seg.b.  taps_stored = the record's tap count (d_taps is zero-padded to at least 128 floats).
 int launch_dec_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_taps, Seg2 seg, void *d_out, long long num,
-                    long long *done, const char **name) {
+                    long long *done, const char **name, const float *h_taps) {
     *done = 0;
     *name = cplx ? "fir_direct" : "fir_tile";
     if ((((uintptr_t)seg.a) & 15) != 0) return SDR_OK;   // TMA bulk copies need a 16-byte aligned source; any output alignment
-    const int T = taps_stored <= 32 ? 32 : taps_stored <= 64 ? 64 : taps_stored <= 128 ? 128 : 0;
-    if (T == 0) return SDR_OK;
+    if (taps_stored > 128) {
+        // 129..256 taps: the taps cannot live in registers -- they travel as launch parameters and reach every FFMA / FFMA2
+        // as a uniform-register operand (h_taps: the record's host copy, zero-padded here).  78 registers instead of 168.
+        // FP32-pipe bound at decimation 4 and 8 (128 / 64 FMA per complex input sample), HBM-bound at 16.
+        if (!(taps_stored <= 256 && h_taps && (D == 4 || D == 8 || D == 16))) return SDR_OK;
+        float padded[256] = {0.0f};
+        for (int k = 0; k < taps_stored; k++) padded[k] = h_taps[k];
+#define SDR_RING_P(CP, DD, RR, label)                                                     \
+        if (cplx == CP && D == DD) { *name = label; return launch_ring<CP, 256, DD, RR, true>(c, d_taps, seg, d_out, num, done, padded); }
+        SDR_RING_P(true, 8, 8, "dec_c_ring<256,8,8,param>")
+        SDR_RING_P(true, 4, 8, "dec_c_ring<256,4,8,param>")
+        SDR_RING_P(true, 16, 4, "dec_c_ring<256,16,4,param>")
+        SDR_RING_P(false, 8, 8, "dec_r_ring<256,8,8,param>")
+        SDR_RING_P(false, 4, 8, "dec_r_ring<256,4,8,param>")
+        SDR_RING_P(false, 16, 8, "dec_r_ring<256,16,8,param>")
+#undef SDR_RING_P
+        return SDR_OK;
+    }
+    const int T = taps_stored <= 32 ? 32 : taps_stored <= 64 ? 64 : 128;
 #define SDR_RING(CP, TT, DD, RR, label)                                                     \
     if (cplx == CP && T == TT && D == DD) { *name = label; return launch_ring<CP, TT, DD, RR>(c, d_taps, seg, d_out, num, done); }
     SDR_RING(true, 128, 8, 8, "dec_c_ring<128,8,8>")

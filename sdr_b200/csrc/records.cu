@@ -103,7 +103,7 @@ int FirRec::run(Seg2 seg, long long first, void *d_out, long long num, bool cros
         if (can_fork && !covers) { SDR_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream)); fork_recorded = true; }
         const char *name = nullptr;
         if (D <= 2) SDR_TRY(launch_fir_small_stride_fast(ctx, cplx, T, D, d_taps, seg.a, seg.na, d_out, num, &done, &name));
-        else        SDR_TRY(launch_dec_fast(ctx, cplx, T, D, d_taps, seg, d_out, num, &done, &name));
+        else        SDR_TRY(launch_dec_fast(ctx, cplx, T, D, d_taps, seg, d_out, num, &done, &name, h_taps.empty() ? nullptr : h_taps.data()));
         if (done > 0) last_kernel = name;
     }
     if (done == 0 && seg.nb > 0) {
@@ -150,7 +150,7 @@ int FirRec::run_tuned(const void *d_in, long long n_in, long long first, void *d
         long long fit = seg.na >= T ? (seg.na - T) / D + 1 : 0;
         if (fit < num) num = fit;
     }
-    SDR_TRY(launch_dec_fast(ctx, cplx, T, D, d_taps, seg, d_out, num, done, &name));
+    SDR_TRY(launch_dec_fast(ctx, cplx, T, D, d_taps, seg, d_out, num, done, &name, h_taps.empty() ? nullptr : h_taps.data()));
     if (*done > 0) last_kernel = name;
     return SDR_OK;
 }
@@ -319,6 +319,7 @@ static int oneshot_fir(const char *who, int kind, bool cplx, int num, int factor
     SDR_CUDA(cudaMemcpyAsync(d_base + taps_bytes, in, in_bytes, cudaMemcpyHostToDevice, c->stream));
     FirRec r;
     r.ctx = c; r.cplx = cplx; r.D = factor; r.T = T; r.d_taps = (float *)d_base; r.d_ex_taps = r.d_taps;
+    r.h_taps.assign(full.begin(), full.begin() + T);
     r.arith = (force_exact_variant >= 0) ? SDR_ARITH_EXACT : default_arith();
     // EXACT: the AVX member of the family this entry point stands in for
     r.ex_W = 8; r.ex_sym = (kind == K_SYM); r.ex_T = (kind == K_SYM) ? numCoeffs : T;

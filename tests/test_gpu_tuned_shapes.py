@@ -48,6 +48,8 @@ def taps_for(n, seed):
 FM = np.load(os.path.join(HERE, "golden", "fm_example_coeffs.npz"))
 
 SHAPES = [(cplx, T, D) for cplx in (True, False) for T in (32, 51, 64, 100, 128) for D in (1, 2, 4, 8, 16)]
+# 129..256 taps, decimation 4 / 8 / 16: the ring kernels with their taps as launch parameters
+SHAPES += [(cplx, T, D) for cplx in (True, False) for T in (256, 200) for D in (4, 8, 16)] + [(True, 132, 8)]
 
 
 @pytest.mark.parametrize("cplx,T,D", SHAPES)

@@ -41,8 +41,10 @@ def main():
     for cplx in (True, False):
         ne = n if cplx else 2 * n
         eb = 8 if cplx else 4
-        for T in (32, 51, 64, 128):
+        for T in (32, 51, 64, 128, 256):
             for D in (1, 2, 4, 8, 16):
+                if T == 256 and D < 4:
+                    continue          # 129..256 taps: decimators only (taps as launch parameters)
                 taps = fm["coeffsRFDecim"] if T == 51 else (rng.standard_normal(T) / 8).astype(np.float32)
                 sm = 8 if (D == 1 or not cplx) else 4
                 if D == 1:
@@ -56,7 +58,7 @@ def main():
                 ms = timed(ctx, fn)
                 rate = ne / (ms * 1e-3)
                 bps = eb + eb / D
-                Tk = 32 if Ts <= 32 else 64 if Ts <= 64 else 128
+                Tk = 32 if Ts <= 32 else 64 if Ts <= 64 else 128 if Ts <= 128 else 256
                 fma = (2 if cplx else 1) * Tk / D      # lane-FMAs per input element the kernel issues (its tap capacity)
                 print(json.dumps({"data": "complex" if cplx else "real", "taps": T, "stored": Ts, "D": D, "kernel": rec.last_kernel(),
                                   "ms": round(ms, 4), "Gsamples_per_s": round(rate / 1e9, 1), "hbm_frac": round(rate * bps / 1e9 / PEAK, 3),
