@@ -26,7 +26,7 @@ namespace sdr {
 // capacity: a record with fewer taps runs on the next larger instantiation with its tap array zero-padded (FirRec keeps
 // d_taps padded to 128 floats), so e.g. the FM example's 51-tap RF decimator (examples/fm/Coeffs.hs:11-66) is the <64, 8>
 // kernel.  T need not be a multiple of D.
-template <bool CPLX, int T, int D, int R>
+template <bool CPLX, int T, int D, int R, int NW = 8>
 struct RingCfg {
     static constexpr int EB = CPLX ? 8 : 4;                 // bytes per stream element
     static constexpr int EPC = 16 / EB;                     // elements per 16-byte chunk (one LDS.128)
@@ -40,13 +40,13 @@ struct RingCfg {
     static constexpr int NCH = (WIN + EPC - 1) / EPC;       // ... as 16-byte chunks
     static constexpr int HALO_RAW = (NCH * EPC - SEG_ELEMS + SEG_ELEMS - 1) / SEG_ELEMS;
     static constexpr int HALO_SEGS = HALO_RAW < 1 ? 1 : HALO_RAW;   // segments of the NEXT sub-tile a pass reads
-    static constexpr int NWARPS = 8;
+    static constexpr int NWARPS = NW;
     static constexpr int NS_FIT = (220 * 1024 - HALO_SEGS * SEG_STRIDE - 256) / SLOT_BYTES;
     static constexpr int NS = NS_FIT >= 2 * NWARPS ? 2 * NWARPS : NS_FIT;                  // ring slots
     static constexpr bool GUARD = (NS % NWARPS) != 0;   // see slot_wait in ring_common.cuh
     static constexpr int RING_BYTES = NS * SLOT_BYTES + HALO_SEGS * SEG_STRIDE;           // + mirror of slot 0's head
     static constexpr int SMEM_BYTES = RING_BYTES + 2 * NS * 8 + NS * 4 + 256;
-    static_assert(NS >= NWARPS + 3, "ring too small for 8 warps plus prefetch");
+    static_assert(NS >= NWARPS + 3, "ring too small for the warps plus prefetch");
     static_assert(HALO_SEGS <= 32, "halo wider than a sub-tile");
     static_assert(CPLX ? R % 2 == 0 : R % 4 == 0, "outputs per lane are stored in 16-byte groups");
 };
@@ -54,12 +54,12 @@ struct RingCfg {
 // TP: the taps travel as launch parameters (constant bank) instead of living in registers -- what makes 256 taps fit.
 template <int N> struct TapBlock { float t[N]; };
 
-template <bool CPLX, int T, int D, int R, bool TP = false>
-__global__ void __launch_bounds__(256, 1)
+template <bool CPLX, int T, int D, int R, bool TP = false, int NW = 8>
+__global__ void __launch_bounds__(32 * NW, 1)
 k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restrict__ in_b, long long total_bytes,
            void *__restrict__ out, long long num, const float *__restrict__ taps, long long n_sub,
            const __grid_constant__ TapBlock<TP ? T : 1> K) {
-    typedef RingCfg<CPLX, T, D, R> C;
+    typedef RingCfg<CPLX, T, D, R, NW> C;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
@@ -239,9 +239,9 @@ k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restric
     }
 }
 
-template <bool CPLX, int T, int D, int R, bool TP = false>
+template <bool CPLX, int T, int D, int R, bool TP = false, int NW = 8>
 static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long long num, long long *done, const float *h_taps = nullptr) {
-    typedef RingCfg<CPLX, T, D, R> C;
+    typedef RingCfg<CPLX, T, D, R, NW> C;
     constexpr int EB = C::EB, EPC = C::EPC;
     const long long n_in = seg.na + seg.nb;
     const long long needed = (num - 1) * D + T;                    // elements the `num` outputs read (T = the kernel's tap capacity)
@@ -271,14 +271,14 @@ static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long 
     }
     (void)needed2;
     SDR_TRY(c->bind());
-    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_ring<CPLX, T, D, R, TP>), C::SMEM_BYTES));
+    SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_ring<CPLX, T, D, R, TP, NW>), C::SMEM_BYTES));
     int sms = c->sm_count - c->reserve_sms;
     if (sms < 1) sms = 1;
     int grid = (int)(n_sub < sms ? n_sub : sms);
     const long long num_mask = covering ? num : n_sub * C::SUB_OUT;
     {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = c->s();
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * NW); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = c->s();
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -287,7 +287,7 @@ static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long 
         const void *a0 = seg.a, *b0 = seg.b;
         TapBlock<TP ? T : 1> K = {};
         if (TP) for (int k = 0; k < T; k++) K.t[TP ? k : 0] = h_taps[k];
-        SDR_CUDA(cudaLaunchKernelEx(&cfg, k_dec_ring<CPLX, T, D, R, TP>, a0, a_bytes, b0, total_bytes, d_out, num_mask, d_taps, n_sub, K));
+        SDR_CUDA(cudaLaunchKernelEx(&cfg, k_dec_ring<CPLX, T, D, R, TP, NW>, a0, a_bytes, b0, total_bytes, d_out, num_mask, d_taps, n_sub, K));
     }
     c->launches++;
     SDR_CUDA(cudaGetLastError());
@@ -328,6 +328,19 @@ int launch_dec_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_ta
         return SDR_OK;
     }
     const int T = taps_stored <= 32 ? 32 : taps_stored <= 64 ? 64 : 128;
+    // Real data, 128 taps, decimation 4 / 8: taps as launch parameters (uniform-register operands), which frees the registers
+    // for 16 warps at 8 outputs per lane -- 588 / 1055 Gsamples/s against 506 / 969 for the register-tap form below (which
+    // stays for 64 taps, where it is the faster one: 824 / 1486 against 760 / 1397).  SDR_B200_DEC_TP=0 switches it off,
+    // =2 also takes the 64-tap shapes (measurement knob).
+    static const int tp_mode = getenv("SDR_B200_DEC_TP") ? atoi(getenv("SDR_B200_DEC_TP")) : 1;
+    if (tp_mode && h_taps && !cplx && (D == 4 || D == 8) && (T == 128 || (tp_mode == 2 && T == 64))) {
+        float padded[128] = {0.0f};
+        for (int k = 0; k < taps_stored; k++) padded[k] = h_taps[k];
+        if (T == 128 && D == 8) { *name = "dec_r_ring<128,8,8,param,16w>"; return launch_ring<false, 128, 8, 8, true, 16>(c, d_taps, seg, d_out, num, done, padded); }
+        if (T == 128 && D == 4) { *name = "dec_r_ring<128,4,8,param,16w>"; return launch_ring<false, 128, 4, 8, true, 16>(c, d_taps, seg, d_out, num, done, padded); }
+        if (T == 64 && D == 4) { *name = "dec_r_ring<64,4,8,param,16w>"; return launch_ring<false, 64, 4, 8, true, 16>(c, d_taps, seg, d_out, num, done, padded); }
+        if (T == 64 && D == 8) { *name = "dec_r_ring<64,8,8,param,16w>"; return launch_ring<false, 64, 8, 8, true, 16>(c, d_taps, seg, d_out, num, done, padded); }
+    }
 #define SDR_RING(CP, TT, DD, RR, label)                                                     \
     if (cplx == CP && T == TT && D == DD) { *name = label; return launch_ring<CP, TT, DD, RR>(c, d_taps, seg, d_out, num, done); }
     SDR_RING(true, 128, 8, 8, "dec_c_ring<128,8,8>")

@@ -30,6 +30,9 @@ def main():
     L.check(L.lib.sdr_filter_stream(fc.handle, x.ptr, n, y.ptr, n - 63))
     dr = sdr_b200.cudaDecimatorR(8, sdr_b200.windowed_sinc_taps(128, 1 / 16), ctx=ctx, sizeMultiple=8)
     L.check(L.lib.sdr_decimate_stream(dr.handle, x.ptr, nr, y.ptr, (nr - 128) // 8 + 1))
+    # 256 taps: the ring kernel with its taps as launch parameters
+    d256 = sdr_b200.cudaDecimatorC(8, sdr_b200.windowed_sinc_taps(256, 1 / 16), ctx=ctx, sizeMultiple=4)
+    L.check(L.lib.sdr_decimate_stream(d256.handle, x.ptr, n, y.ptr, (n - 256) // 8 + 1))
     # cfg1, cfg3, complex resampler
     half = sdr_b200.windowed_sinc_taps(64, 1 / 4)[:32]
     f = sdr_b200.cudaFilterSymR(half, ctx=ctx)
