@@ -399,7 +399,7 @@ struct PersistRelay { volatile long long avail; volatile int closed; volatile in
 template <bool CPLX, int T, int D, int R, int PB>
 __global__ void __launch_bounds__(256, 1)
 k_dec_ring_persist(const void *__restrict__ in, void *__restrict__ out, const float *__restrict__ taps, PersistCtl *ctl,
-                   PersistRelay *relay, long long runs_total) {
+                   PersistRelay *relay, long long runs_total, int dbg_flags) {
     typedef RingCfg<CPLX, T, D, R> C;
     static_assert(CPLX, "the persistent consumer is instantiated for complex data");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -495,15 +495,34 @@ k_dec_ring_persist(const void *__restrict__ in, void *__restrict__ out, const fl
             bulk_g2s(ring + C::NS * C::SLOT_BYTES + lane * C::SEG_STRIDE, src, C::SEG_BYTES, bar);
         if (lane == 0) gen_publish(gen_armed + 4 * slot, t / C::NS + 1);
     };
-    // make sure tile t's fill has been issued by exactly one warp: whoever moves the slot's claim word from gen-1 to gen
+    // Make sure tile t's fill gets issued, by exactly one warp: whoever moves the slot's claim word from gen-1 to gen.
+    // The slots are shared between warps (13 slots, 8 warps), so the caller may be AHEAD of the slot's history:
+    //   * the previous generation may not even have been claimed yet (its consumer is behind): nobody else is then
+    //     guaranteed to come back for this tile, so the caller waits for that claim and takes this one itself;
+    //   * the previous generation may be claimed but not landed (its claimer still waits for ITS predecessor's readers).
+    //     The one-bit parity wait on the `empty` barrier below would then alias with the phase two back, return at once
+    //     and let this fill overwrite a slot that is still being read -- and arrive a second time on a `full` barrier
+    //     whose phase is still open (an over-arrival: the kernel dies with "unspecified launch failure").  So first wait,
+    //     generation-guarded, until the previous generation HAS landed; from then on the `empty` barrier is in the phase
+    //     the parity names.
+    // In the steady state the claim was made long ago by the warp that freed the slot and all of this is one shared load.
     auto claim_and_fill = [&](int t) {
         const int slot = t % C::NS, gen = t / C::NS + 1;
         int won = 0;
-        // (a plain look first: in the steady state the fill was claimed long ago by the warp that freed the slot)
-        if (lane == 0 && *(volatile int *)&s_claim[slot] == gen - 1) won = atomicCAS(&s_claim[slot], gen - 1, gen) == gen - 1;
+        if (lane == 0) {
+            for (;;) {
+                const int c = *(volatile int *)&s_claim[slot];
+                if (c >= gen) break;                                          // claimed (the claimer issues the fill)
+                if (c == gen - 1) { if (atomicCAS(&s_claim[slot], gen - 1, gen) == gen - 1) { won = 1; break; } continue; }
+                __nanosleep(64);                                              // the previous generation is still unclaimed
+            }
+        }
         won = __shfl_sync(0xffffffffu, won, 0);
         if (!won) return;
-        if (gen > 1) mbar_wait(bar_empty + 8 * slot, (gen - 2) & 1);   // the previous generation has been consumed
+        if (gen > 1) {
+            slot_wait<true>(bar_full + 8 * slot, gen_armed + 4 * slot, gen - 1);   // the previous generation has landed ...
+            mbar_wait(bar_empty + 8 * slot, (gen - 2) & 1);                        // ... and has been consumed
+        }
         issue_fill(t);
     };
 
@@ -592,7 +611,7 @@ k_dec_ring_persist(const void *__restrict__ in, void *__restrict__ out, const fl
         // opportunistic refill of the slot just freed -- only if the target's run is already published (never waits for input)
         const int t2 = t + C::NS;
         const long long r2 = run_of(t2);
-        if (r2 < runs_total && have_run(r2, false)) claim_and_fill(t2);
+        if (!(dbg_flags & 1) && r2 < runs_total && have_run(r2, false)) claim_and_fill(t2);
     }
     publish_pending();
 }
@@ -611,8 +630,11 @@ static int launch_persist_t(Ctx *c, const float *d_taps, const void *d_in, void 
                             cudaStream_t stream, int grid) {
     typedef RingCfg<true, T, 8, 8> C;
     SDR_TRY(ring_attr(c, reinterpret_cast<const void *>(k_dec_ring_persist<true, T, 8, 8, 32>), C::SMEM_BYTES));
+    // test knob, bit 0: no opportunistic refills -- every fill is then issued by the warp that consumes the tile, the path
+    // the kernel otherwise takes only when it runs ahead of the host (tests/test_gpu_persistent.py runs the suite that way too)
+    static const int dbg_flags = getenv("SDR_B200_PERSIST_FLAGS") ? atoi(getenv("SDR_B200_PERSIST_FLAGS")) : 0;
     k_dec_ring_persist<true, T, 8, 8, 32><<<grid + 1, 256, C::SMEM_BYTES, stream>>>(d_in, d_out, d_taps, (PersistCtl *)ctl,
-                                                                                     (PersistRelay *)d_relay, runs_total);
+                                                                                     (PersistRelay *)d_relay, runs_total, dbg_flags);
     return SDR_OK;
 }
 

@@ -199,3 +199,21 @@ def test_persistent_consumer_idle_wind_down_and_self_disable(sdr, ctx):
     dbuf.free()
     y = np.concatenate(got)
     assert len(y) == len(want) and np.array_equal(y.view(np.uint32), want.view(np.uint32))
+
+
+def test_persistent_consumer_with_consumer_side_fills_only():
+    """the same suite with SDR_B200_PERSIST_FLAGS=1: no opportunistic refills, every ring fill is issued by the warp that
+    consumes the tile -- the path the kernel otherwise takes only when it runs ahead of the host.  (Round 2 found two bugs
+    there that the normal path hit once in ~40 passes of 32768 pushes: a tile whose previous generation was still
+    unclaimed was never filled, and the one-bit parity wait on a slot's `empty` barrier aliased with the phase two back,
+    which let a fill over-arrive on an open `full` phase: "unspecified launch failure".)"""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("SDR_B200_PERSIST_FLAGS"):
+        pytest.skip("already running in that mode")
+    env = dict(os.environ, SDR_B200_PERSIST_FLAGS="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_persistent.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "equals_launch_path or request_response or fm_example"], env=env, capture_output=True, text=True, timeout=110)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
