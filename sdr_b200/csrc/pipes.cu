@@ -30,10 +30,12 @@ struct LinBuf {
     char *p = nullptr;
     size_t cap = 0, rd = 0, wr = 0;
     bool fixed = false;   // a persistent consumer writes into this buffer: it must neither move nor rewind
+    bool borrowed = false; // the memory is the caller's output buffer for the duration of one sdr_pipe_run: not ours to move or free
     size_t size() const { return wr - rd; }
     int reserve(size_t more) {   // make room for `more` bytes after wr, keeping [rd, wr)
         if (wr + more <= cap) return SDR_OK;
         if (fixed) return set_error(SDR_ENOMEM, "buffer is held in place by a persistent consumer session (%zu more bytes wanted)", more);
+        if (borrowed) return set_error(SDR_ENOMEM, "borrowed output buffer exhausted (%zu more bytes wanted)", more);
         size_t live = size();
         if (live + more <= cap && rd >= live) {   // slide the live region to the front (regions do not overlap)
             if (live) SDR_CUDA(cudaMemcpyAsync(p, p + rd, live, cudaMemcpyDeviceToDevice, c->stream));
@@ -49,7 +51,7 @@ struct LinBuf {
         p = np; cap = ncap; rd = 0; wr = live;
         return SDR_OK;
     }
-    void consume(size_t bytes) { rd += bytes; if (rd == wr && !fixed) rd = wr = 0; }
+    void consume(size_t bytes) { rd += bytes; if (rd == wr && !fixed && !borrowed) rd = wr = 0; }
     // move the (small) live region so that it starts `lead` bytes past a 16-byte boundary at the front of the buffer;
     // skipped when source and destination would overlap
     int realign(size_t lead) {
@@ -60,7 +62,7 @@ struct LinBuf {
         rd = lead; wr = lead + live;
         return SDR_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = rd = wr = 0; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = rd = wr = 0; }
 };
 
 // Tracing aid.  SDR_B200_TRACE=1: synchronise around every stage step and print its wall time (serialises the stream).
@@ -134,6 +136,7 @@ struct sdr_pipe {
     long long block_out = 0;          // FIR kinds: elements per yielded vector
     LinBuf in;                        // FIR kinds: carried tail + pushed data
     LinBuf fifo;                      // produced, not yet popped / forwarded
+    LinBuf fifo_own;                  // the stage's own FIFO while `fifo` is the caller's output buffer (sdr_pipe_run, device output)
     std::deque<long long> vec_lens;   // element-wise kinds: lengths of the queued vectors
     // resampler stream bookkeeping (global indices)
     long long k_next = 0;             // next output index
@@ -220,9 +223,28 @@ static int materialize_ext(sdr_pipe *p) {
 // appends behind the region, so the next hand-over is adjacent and extends the run, until it runs out of room -- only then
 // does the downstream stage take what it still references into its own buffer.
 static bool fifo_leased(const sdr_pipe *p) { return p->downstream && p->downstream->ext_fwd && p->downstream->ext_bytes > 0; }
+// sdr_pipe_run with a device output buffer lets the sink stage produce STRAIGHT INTO that buffer (no copy of the yielded
+// vectors): the stage's FIFO is the caller's memory for the duration of the call.  fifo_return gives it back: what has not
+// been yielded yet (the partial output block, or everything still undrained when the buffer runs out) moves into the
+// stage's own FIFO.
+static int fifo_return(sdr_pipe *p) {
+    if (!p->fifo.borrowed) return SDR_OK;
+    LinBuf b = p->fifo;
+    p->fifo = p->fifo_own;
+    p->fifo_own = LinBuf();
+    p->fifo.rd = p->fifo.wr = 0;
+    const size_t live = b.size();
+    if (live) {
+        SDR_TRY(p->fifo.reserve(live));
+        SDR_CUDA(cudaMemcpyAsync(p->fifo.p, b.p + b.rd, live, cudaMemcpyDeviceToDevice, p->ctx->stream));
+        p->fifo.wr = live;
+    }
+    return SDR_OK;
+}
 static int fifo_reserve(sdr_pipe *p, size_t bytes) {
+    if (p->fifo.borrowed && p->fifo.wr + bytes > p->fifo.cap) SDR_TRY(fifo_return(p));   // the caller's buffer is too small to work in
     if (fifo_leased(p) && p->fifo.wr + bytes > p->fifo.cap) SDR_TRY(materialize_ext(p->downstream));
-    if (!fifo_leased(p) && p->fifo.rd == p->fifo.wr && !p->fifo.fixed) p->fifo.rd = p->fifo.wr = 0;
+    if (!fifo_leased(p) && p->fifo.rd == p->fifo.wr && !p->fifo.fixed && !p->fifo.borrowed) p->fifo.rd = p->fifo.wr = 0;
     return p->fifo.reserve(bytes);
 }
 // `bytes` at the front of the FIFO have been handed to the downstream stage
@@ -1079,6 +1101,8 @@ static int drain(sdr_pipe *sink, void *out, long long out_capacity, int out_mem,
                                      cudaMemcpyDeviceToHost, sink->ctx->side));
             SDR_CUDA(cudaEventRecord(sink->ev_out_done, sink->ctx->side));
             sink->d2h_outstanding = true;
+        } else if (sink->fifo.borrowed && sink->fifo.p + sink->fifo.rd == (char *)out + (size_t)*written * sink->out_eb) {
+            // produced in place: the vectors already are where the caller wants them
         } else {
             SDR_CUDA(cudaMemcpyAsync((char *)out + (size_t)*written * sink->out_eb, sink->fifo.p + sink->fifo.rd, (size_t)n * sink->out_eb,
                                      out_mem == SDR_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, sink->ctx->stream));
@@ -1118,6 +1142,24 @@ int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_
         sdr_pipe *p; bool armed;
         ~Quiesce() { if (armed) { flush_pending(p); cudaStreamSynchronize(p->ctx->stream); cudaStreamSynchronize(p->ctx->side); } }
     } quiesce{p, true};
+    // Device output: a FIR-kind sink produces straight into the caller's buffer (see fifo_return).  Whatever the stage
+    // still holds from an earlier call (a partial output block) goes in front.  Given back on every exit path.
+    struct Borrow {
+        sdr_pipe *s;
+        ~Borrow() { if (s && s->fifo.borrowed) { if (s->ps.open) persist_close(s); fifo_return(s); } }   // (error exits only)
+    } borrow{nullptr};
+    if (out_mem == SDR_DEVICE && is_fir_kind(sink->kind) && !sink->ps.open && !sink->downstream && !sink->fifo.borrowed &&
+        (((uintptr_t)out) & 15) == 0 && sink->fifo.size() <= (size_t)out_capacity * sink->out_eb) {
+        SDR_TRY(flush_pending(sink));
+        SDR_TRY(fifo_writable(sink));
+        const size_t live = sink->fifo.size();
+        if (live) SDR_CUDA(cudaMemcpyAsync(out, sink->fifo.p + sink->fifo.rd, live, cudaMemcpyDeviceToDevice, sink->ctx->stream));
+        sink->fifo_own = sink->fifo;
+        LinBuf b;
+        b.c = sink->ctx; b.p = (char *)out; b.cap = (size_t)out_capacity * sink->out_eb; b.rd = 0; b.wr = live; b.borrowed = true;
+        sink->fifo = b;
+        borrow.s = sink;
+    }
     for (long long v = 0; v < n_vecs; v++) {
         SDR_TRY(pipe_push_any(p, (const char *)in + (size_t)(v * vec_len) * p->in_eb, vec_len, in_mem));
         SDR_TRY(drain(sink, out, out_capacity, out_mem, &written));
@@ -1128,6 +1170,7 @@ int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_
         if (q == sink) break;
     }
     SDR_TRY(drain(sink, out, out_capacity, out_mem, &written));
+    SDR_TRY(fifo_return(sink));
     auto t_issued = std::chrono::steady_clock::now();
     SDR_TRY(sdr_pipe_sync(p));
     if (trace_mode())

@@ -210,3 +210,47 @@ def test_connected_stage_keeps_handed_over_vectors_in_the_upstream_fifo(sdr, ctx
     for p in ((lo, fe) if order == "down_first" else (fe, lo)):
         p.close()
     dbuf.free(); out.free()
+
+
+@pytest.mark.parametrize("slack", [8192, 0, -1])
+def test_pipe_run_produces_straight_into_a_device_output_buffer(sdr, ctx, slack):
+    """sdr_pipe_run with a device output buffer: the sink stage works IN the caller's buffer (no copy of the yielded
+    vectors).  Two runs through one stage -- the partial output block the first run leaves goes in front in the second --
+    with ample capacity, with exactly the capacity the yielded vectors need (the partial block does not fit: the stage takes
+    its FIFO back mid-run and copies from there on) and one element less (an error, not an overrun).  Same vectors as
+    host pushes / pops."""
+    from sdr_b200 import _lib as L
+    taps = synth.windowed_sinc_taps(128, 1 / 16)
+    vec, nvec = 8192 + 6, 37
+    x = synth.noise_complex(vec * nvec * 2, first=21)
+    d = sdr.cudaDecimatorC(8, taps, sizeMultiple=4)
+    ref_pipe = sdr.pipeFirDecimator(d, 1000)
+    ref = [[], []]
+    for run in range(2):
+        for i in range(nvec):
+            ref_pipe.push(x[(run * nvec + i) * vec:(run * nvec + i + 1) * vec])
+            _drain(ref_pipe, ref[run])
+    ref_pipe.close()
+    p = sdr.pipeFirDecimator(d, 1000)
+    dbuf = ctx.to_device(x)
+    n_out = C.c_longlong()
+    for run in range(2):
+        want = np.concatenate(ref[run])
+        cap = len(want) + slack
+        out = ctx.alloc(8 * (len(want) + 8192) + 64)
+        L.check(L.lib.sdr_memset_dev(ctx.h, out.ptr, 0xff, 8 * (len(want) + 8192)))
+        rc = L.lib.sdr_pipe_run(p.h, p.h, dbuf.at(8 * run * nvec * vec), vec, nvec, L.SDR_DEVICE_HELD, out.ptr, cap, L.SDR_DEVICE, C.byref(n_out))
+        if slack < 0:
+            assert rc != 0            # capacity too small for the yielded vectors
+            out.free()
+            break
+        L.check(rc)
+        assert n_out.value == len(want)
+        got = out.to_host(np.complex64, len(want))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        if slack == 0:                # nothing may have been written behind the capacity
+            tail = out.to_host(np.uint32, 16, offset_bytes=8 * cap)
+            assert np.all(tail == 0xffffffff)
+        out.free()
+    p.close()
+    dbuf.free()
