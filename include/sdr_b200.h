@@ -327,7 +327,10 @@ int sdr_pipe_set_batch(sdr_pipe_t *p, long long min_outputs);
 int sdr_pipe_set_persistent(sdr_pipe_t *p, long long max_session_samples);
 /* `runEffect $ each vectors >-> p >-> ... >-> sink >-> collect` as one native loop: pushes n_vecs consecutive vectors of
  * vec_len input elements starting at `in` into `p`, pops every vector `sink` yields (sink = p, or the last stage
- * connected behind it) into `out` back to back, then sdr_pipe_sync.  *n_out = elements written (<= out_capacity). */
+ * connected behind it) into `out` back to back, then sdr_pipe_sync.  *n_out = elements written (<= out_capacity).
+ * With out_mem == SDR_DEVICE a FIR-kind sink produces straight into `out` (no copy of the yielded vectors): the elements
+ * between *n_out and out_capacity are then scratch (they may hold the partial output block that the stage keeps for the
+ * next call).  Nothing is ever written past out_capacity. */
 int sdr_pipe_run(sdr_pipe_t *p, sdr_pipe_t *sink, const void *in, long long vec_len, long long n_vecs, int in_mem,
                  void *out, long long out_capacity, int out_mem, long long *n_out);
 /* Producer / consumer edges on file descriptors, the steps either side of the path:
