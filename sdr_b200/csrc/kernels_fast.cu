@@ -51,15 +51,16 @@ int launch_dec_fast(Ctx *c, bool cplx, int taps_stored, int D, const float *d_ta
         return SDR_OK;
     }
     const int T = taps_stored <= 32 ? 32 : taps_stored <= 64 ? 64 : 128;
-    // Real data, 128 taps, decimation 4 / 8: taps as launch parameters (uniform-register operands), which frees the registers
-    // for 16 warps at 8 outputs per lane -- 588 / 1055 Gsamples/s against 506 / 969 for the register-tap form (which stays
-    // for 64 taps, where it is the faster one: 824 / 1486 against 760 / 1397).  SDR_B200_DEC_TP=0 switches it off, =2 also
-    // takes the 64-tap shapes (measurement knob).
+    // 128 taps, real data at decimation 4 / 8 and complex data at decimation 4: taps as launch parameters (uniform-register
+    // operands), which frees the registers for 16 warps at 8 outputs per lane -- real 588 / 1055 Gsamples/s against 506 / 969
+    // for the register-tap form, complex 432 against 380 (the register form stays for 64 taps, where it is the faster one:
+    // 824 / 1486 against 760 / 1397, and for complex decimation 8 / 16, which sit at the HBM roofline).
+    // SDR_B200_DEC_TP=0 switches it off, =2 also takes the real 64-tap shapes (measurement knob).
     static const int tp_mode = getenv("SDR_B200_DEC_TP") ? atoi(getenv("SDR_B200_DEC_TP")) : 1;
-    if (tp_mode && h_taps && !cplx && (D == 4 || D == 8) && (T == 128 || (tp_mode == 2 && T == 64))) {
+    if (tp_mode && h_taps && ((!cplx && (D == 4 || D == 8) && (T == 128 || (tp_mode == 2 && T == 64))) || (cplx && D == 4 && T == 128))) {
         float padded[128] = {0.0f};
         for (int k = 0; k < taps_stored; k++) padded[k] = h_taps[k];
-        SDR_TRY(launch_ring_param(c, false, T, D, d_taps, padded, seg, d_out, num, done, &label));
+        SDR_TRY(launch_ring_param(c, cplx, T, D, d_taps, padded, seg, d_out, num, done, &label));
         if (label) { *name = label; return SDR_OK; }
     }
     if (cplx) SDR_TRY(launch_ring_complex(c, T, D, d_taps, seg, d_out, num, done, &label));

@@ -21,6 +21,7 @@ int launch_ring_param(Ctx *c, bool cplx, int T, int D, const float *d_taps, cons
     if (T == 128 && !cplx && D == 4) { *name = "dec_r_ring<128,4,8,param,16w>"; return launch_ring<false, 128, 4, 8, true, 16>(c, d_taps, seg, d_out, num, done, h_taps); }
     if (T == 64 && !cplx && D == 4) { *name = "dec_r_ring<64,4,8,param,16w>"; return launch_ring<false, 64, 4, 8, true, 16>(c, d_taps, seg, d_out, num, done, h_taps); }
     if (T == 64 && !cplx && D == 8) { *name = "dec_r_ring<64,8,8,param,16w>"; return launch_ring<false, 64, 8, 8, true, 16>(c, d_taps, seg, d_out, num, done, h_taps); }
+    if (T == 128 && cplx && D == 4) { *name = "dec_c_ring<128,4,8,param,16w>"; return launch_ring<true, 128, 4, 8, true, 16>(c, d_taps, seg, d_out, num, done, h_taps); }
     return SDR_OK;
 }
 
