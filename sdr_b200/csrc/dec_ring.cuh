@@ -279,6 +279,8 @@ static int launch_ring(Ctx *c, const float *d_taps, Seg2 seg, void *d_out, long 
     int sms = c->sm_count - c->reserve_sms;
     if (sms < 1) sms = 1;
     int grid = (int)(n_sub < sms ? n_sub : sms);
+    static const int grid_override = getenv("SDR_B200_GRID") ? atoi(getenv("SDR_B200_GRID")) : 0;   // measurement knob
+    if (grid_override > 0 && grid_override < grid) grid = grid_override;
     const long long num_mask = covering ? num : n_sub * C::SUB_OUT;
     {
         cudaLaunchConfig_t cfg = {};

@@ -125,6 +125,8 @@ struct PersistSession {
     size_t fifo_base = 0;                        // FIFO offset of run 0's outputs
     long long capacity_bytes = 0;
     const char *kernel = "none";
+    cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;  // SDR_B200_PERSIST_DEBUG: device time of the resident kernel
+    std::chrono::steady_clock::time_point t_open;
 };
 
 struct sdr_pipe {
@@ -301,7 +303,15 @@ static int persist_close(sdr_pipe *p) {
     __sync_synchronize();
     h->closed = 1;
     __sync_synchronize();
+    auto t_close = std::chrono::steady_clock::now();
     SDR_CUDA(cudaStreamSynchronize(S.stream));
+    if (dbg && S.dbg0) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, S.dbg0, S.dbg1);
+        fprintf(stderr, "[persist] resident kernel %.1f us on the device; host: open -> close request %.1f us, close request -> kernel gone %.1f us\n", ms * 1e3,
+                std::chrono::duration<double, std::micro>(t_close - S.t_open).count(),
+                std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_close).count());
+    }
     persist_poll(p);
     S.open = false;
     p->fifo.fixed = false;
@@ -368,8 +378,15 @@ static int persist_try(sdr_pipe *p, bool *taken) {
         // everything enqueued on the ctx stream so far (what produced the FIFO's contents, tail copies) precedes the consumer
         SDR_CUDA(cudaEventRecord(S.ev, p->ctx->stream));
         SDR_CUDA(cudaStreamWaitEvent(S.stream, S.ev, 0));
+        static const bool dbg_t = getenv("SDR_B200_PERSIST_DEBUG") != nullptr;
+        if (dbg_t) {
+            if (!S.dbg0) { SDR_CUDA(cudaEventCreate(&S.dbg0)); SDR_CUDA(cudaEventCreate(&S.dbg1)); }
+            SDR_CUDA(cudaEventRecord(S.dbg0, S.stream));
+            S.t_open = std::chrono::steady_clock::now();
+        }
         SDR_TRY(launch_dec_persist(p->ctx, f.T, f.D, f.cplx, f.d_taps, S.base, p->fifo.p + S.fifo_base, d_ctl, S.d_relay, runs_total, S.stream,
                                    &S.grid, &S.kernel));
+        if (dbg_t) SDR_CUDA(cudaEventRecord(S.dbg1, S.stream));
         p->fifo.fixed = true;
         S.open = true;
         f.last_kernel = S.kernel;
