@@ -24,4 +24,4 @@ try:
 except Exception as e: print(sys.argv[1], 'ERR', e)
 PY
 done
-tail -3 $O/r2_scale_n*.err
+for f in $O/r2_scale_n*.err; do tail -n 2 $f; done
