@@ -57,6 +57,7 @@ struct RingCfg {
 
 // TP: the taps travel as launch parameters (constant bank) instead of living in registers -- what makes 256 taps fit.
 template <int N> struct TapBlock { float t[N]; };
+__device__ __forceinline__ u64 dup2_bits(float v) { const unsigned int u = __float_as_uint(v); return ((u64)u << 32) | (u64)u; }
 
 template <bool CPLX, int T, int D, int R, bool TP = false, int NW = 8>
 __global__ void __launch_bounds__(32 * NW, 1)
@@ -162,6 +163,7 @@ k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restric
         for (int k = 0; k < (TP ? 1 : T); k++) tap[k] = __ldg(taps + k);
     }
 #define SDR_TAP(k) (TP ? K.t[TP ? (k) : 0] : tap[TP ? 0 : (k)])
+#define SDR_DUP(v) (TP ? dup2_bits(v) : dup2(v))
 
     for (int u = warp; u < cnt; u += C::NWARPS) {
         const int slot = u % C::NS, par = (u / C::NS) & 1;
@@ -182,8 +184,8 @@ k_dec_ring(const void *__restrict__ in, long long a_bytes, const void *__restric
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const int k0 = e0 - r * D, k1 = e0 + 1 - r * D;
-                    if (k0 >= 0 && k0 < T) acc[r] = ffma2(v.x, dup2(SDR_TAP(k0 < 0 ? 0 : (k0 >= T ? 0 : k0))), acc[r]);
-                    if (k1 >= 0 && k1 < T) acc[r] = ffma2(v.y, dup2(SDR_TAP(k1 < 0 ? 0 : (k1 >= T ? 0 : k1))), acc[r]);
+                    if (k0 >= 0 && k0 < T) acc[r] = ffma2(v.x, SDR_DUP(SDR_TAP(k0 < 0 ? 0 : (k0 >= T ? 0 : k0))), acc[r]);
+                    if (k1 >= 0 && k1 < T) acc[r] = ffma2(v.y, SDR_DUP(SDR_TAP(k1 < 0 ? 0 : (k1 >= T ? 0 : k1))), acc[r]);
                 }
             }
             u64 *os = reinterpret_cast<u64 *>(out) + m0;
