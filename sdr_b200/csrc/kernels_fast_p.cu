@@ -10,7 +10,7 @@ int launch_ring_param_c256_d4(Ctx *c, const float *d_taps, const float *h_taps, 
 int launch_ring_param(Ctx *c, bool cplx, int T, int D, const float *d_taps, const float *h_taps, Seg2 seg, void *d_out, long long num,
                       long long *done, const char **name) {
     *done = 0;
-    // (the two instantiations ptxas needs four minutes each for have a translation unit of their own: kernels_fast_p8.cu, _p4.cu)
+    // (the two instantiations the compiler front end needs two minutes each for have a translation unit of their own: kernels_fast_p8.cu, _p4.cu)
     if (T == 256 && cplx == true && D == 8) { *name = "dec_c_ring<256,8,8,param>"; return launch_ring_param_c256_d8(c, d_taps, h_taps, seg, d_out, num, done); }
     if (T == 256 && cplx == true && D == 4) { *name = "dec_c_ring<256,4,8,param>"; return launch_ring_param_c256_d4(c, d_taps, h_taps, seg, d_out, num, done); }
     if (T == 256 && cplx == true && D == 16) { *name = "dec_c_ring<256,16,4,param>"; return launch_ring<true, 256, 16, 4, true>(c, d_taps, seg, d_out, num, done, h_taps); }

@@ -1,5 +1,5 @@
 // one instantiation: complex data, 256 taps as launch parameters, decimate by 4 (dec_ring.cuh; dispatched from kernels_fast_p.cu).
-// On its own because ptxas spends four minutes on its 2048-FFMA2 basic blocks.
+// On its own because the compiler front end spends two minutes on its fully unrolled 2048-FFMA2 blocks.
 #include "dec_ring.cuh"
 
 namespace sdr {
